@@ -1,0 +1,180 @@
+/* mvtv.h -- C ABI of the B200-native MultivarTV hot path (libmvtv_b200.so).
+ *
+ * Drop-in boundary for the mesh-based ADMM solver of brayano/MultivarTV.  Every entry point cites the
+ * reference interface it replaces (paths relative to the upstream repository root).  Plain pointers
+ * and sizes only; all pointers are HOST pointers unless the name ends in _dev.  The caller owns every
+ * host buffer; a plan owns its device memory, stream and (optional) NCCL communicator.  One plan per
+ * host thread.  There is NO CPU fallback: every function returns MVTV_ERR_CUDA if no sm_100 device /
+ * driver is usable.
+ *
+ * Layout conventions (identical to the reference):
+ *   data   n x p doubles, COLUMN-major (arma::mat, cpp-code/solvers.hpp:89)
+ *   theta  N = prod(m) doubles, mesh flattened column-major, axis 0 fastest (cpp-code/utils.cpp:40-52)
+ *   u      R doubles, rows of D in create_D order (cpp-code/utils.cpp:245-269): all-ones mask block first,
+ *          then masks 1..K-1 of fd_binaries; inside a block rows follow the column-major enumeration of
+ *          the vertices that own a forward difference (cpp-code/utils.cpp:103-127)
+ *   axes   concatenated per-axis knot vectors (m[0] + ... + m[p-1] doubles, each ascending); the
+ *          tensor-product mesh of create_mesh (cpp-code/utils.cpp:271-298) is axes[k][i_k]
+ */
+#ifndef MVTV_H
+#define MVTV_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVTV_ABI_VERSION 1
+#define MVTV_MAXP 4
+
+/* status codes */
+#define MVTV_OK 0
+#define MVTV_ERR_INVALID 1        /* bad argument */
+#define MVTV_ERR_CUDA 2           /* CUDA / NCCL failure, or no usable device (no CPU fallback) */
+#define MVTV_ERR_NOT_CONVERGED 3  /* counter exceeded max_counter: CPP mode = the reference's
+                                     throw std::invalid_argument("Failed to converge!")
+                                     (cpp-code/solvers.cpp:122-124); RCPP mode = message + break
+                                     (rcpp solvers.cpp:129-132; outputs are still filled) */
+#define MVTV_ERR_DIM_MISMATCH 4   /* reference operator undefined: non-conforming sparse product for a
+                                     non-cubic mesh with p>=3 (cpp-code/utils.cpp:187,216) */
+#define MVTV_ERR_UNSUPPORTED 5
+#define MVTV_ERR_INNER_SOLVE 6    /* x-update did not reach cg_rtol within cg_maxit */
+
+/* solver modes = the three sibling implementations of the same loop */
+#define MVTV_MODE_CPP 0   /* cpp-code/solvers.cpp:90-130  (int rho, fixed matrix, |dtheta| stop) */
+#define MVTV_MODE_RCPP 1  /* rcpp-code/MultivarTV/src/solvers.cpp:96-136 (double rho, residual stop) */
+#define MVTV_MODE_PY 2    /* code/solvers.py:54-76 (fixed rho = lambda, |dtheta| stop) */
+
+/* operator variants */
+#define MVTV_VARIANT_REFERENCE 0 /* mixedpartial first factor along axis 0 (cpp-code/utils.cpp:187) */
+#define MVTV_VARIANT_INTENDED 1  /* the commented-out intent (cpp-code/utils.cpp:186) */
+
+#define MVTV_F64 64
+#define MVTV_F32 32
+
+/* x-update preconditioner for the matrix-free CG that replaces arma::spsolve (cpp-code/solvers.cpp:116) */
+#define MVTV_PRECOND_JACOBI 0
+#define MVTV_PRECOND_MG 1
+
+/* flags for mvtv_solve */
+#define MVTV_WARM_THETA_FROM_PLAN 1u /* theta_init ignored: continue from the theta left on the device */
+#define MVTV_WARM_U_FROM_PLAN 2u     /* RCPP: u (and its lazy scale) continue from the device state */
+
+typedef struct mvtv_plan mvtv_plan;
+
+typedef struct {
+  int32_t struct_size;   /* sizeof(mvtv_plan_desc) */
+  int32_t p;             /* number of covariates / mesh axes, 1..MVTV_MAXP */
+  int64_t m[MVTV_MAXP];  /* mesh dims ("vec m", cpp-code/solvers.hpp:89) */
+  int32_t dtype;         /* MVTV_F64 | MVTV_F32 (storage and arithmetic of the iteration) */
+  int32_t variant;       /* MVTV_VARIANT_* */
+  int32_t device;        /* CUDA ordinal, -1 = current device */
+  int32_t rank, world;   /* slab partition of the LAST mesh axis; world==1: single GPU */
+  int32_t reserved;
+  const double *deltas;  /* p mesh widths (create_deltas, cpp-code/utils.cpp:300-307), or NULL:
+                            the stand-alone mbs_one path never sets them -> all block scales 1
+                            (cpp-code/solvers.cpp:141-145) */
+  const void *nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks; NULL when world==1 */
+} mvtv_plan_desc;
+
+typedef struct {
+  int32_t struct_size;  /* sizeof(mvtv_solve_params) */
+  int32_t mode;         /* MVTV_MODE_* */
+  double lambda;        /* tuning parameter (cpp-code/solvers.hpp:85,89) */
+  double rho_init;      /* RCPP: caller's rho (rcpp solvers.hpp:100); NaN -> lambda/5 (rcpp solvers.cpp:209).
+                           Ignored in CPP ((int)lambda, cpp-code/solvers.cpp:108) and PY (lambda). */
+  double rho_matrix0;   /* scalar s of the cached system matrix crossO + s*crossD used until the loop
+                           rebuilds it; NaN -> lambda (cpp-code/solvers.cpp:144, rcpp solvers.cpp:150) */
+  double tol;           /* NaN or <=0 -> the reference's TOL macro (1e-3 cpp/py, 1e-4 rcpp) */
+  int32_t max_counter;  /* 0 -> reference default (2000 / 3000 / 5000) */
+  int32_t max_passes;   /* >0: stop after this many ADMM passes (fixed-budget benchmarking) */
+  double cg_rtol;       /* x-update stops at ||b - M theta|| <= cg_rtol*||b||; <=0 -> 1e-12 (f64) / 1e-5 (f32) */
+  int32_t cg_maxit;     /* 0 -> 20000 (f64) / 1000 (f32; reaching it is not an error in f32) */
+  int32_t precond;      /* MVTV_PRECOND_* */
+  uint32_t flags;       /* MVTV_WARM_* */
+  int32_t reserved;
+} mvtv_solve_params;
+
+typedef struct {
+  int32_t counter;      /* the value the reference prints as "Counter" (cpp-code/solvers.cpp:128) */
+  int32_t passes;       /* ADMM passes executed (= counter-1 in CPP/RCPP mode) */
+  int32_t status;       /* MVTV_OK | MVTV_ERR_NOT_CONVERGED | MVTV_ERR_INNER_SOLVE */
+  int32_t reserved;
+  double rho;           /* final rho (rcpp admm_out.rho, rcpp solvers.hpp:91-95) */
+  double r_norm;        /* last ||primal_residual||_2 */
+  double s_norm;        /* last ||dual_residual||_2 */
+  double max_dtheta;    /* last max|theta - thetaold| (the CPP/PY loop test, cpp-code/solvers.cpp:113) */
+  int64_t inner_iters;  /* CG iterations summed over all passes */
+  double device_seconds;/* CUDA-event time of the ADMM loop on the plan's stream */
+  int64_t kernel_launches; /* kernels of this library launched by this call */
+} mvtv_solve_result;
+
+/* -- library ------------------------------------------------------------------------------------ */
+int mvtv_abi_version(void);
+const char *mvtv_last_error(void);            /* thread-local message of the last failing call */
+int mvtv_device_count(int *count);
+/* 128-byte ncclUniqueId for mvtv_plan_desc.nccl_unique_id: call on one rank, broadcast to the others
+ * (e.g. with torch.distributed), then every rank creates its plan. */
+int mvtv_nccl_unique_id(void *out128);
+
+/* -- plan = operators of create_cache_objects (cpp-code/solvers.cpp:31-41) kept on the device ----- */
+/* Replaces: create_D (cpp-code/utils.cpp:245-269) -- D is never materialised, only its block table. */
+int mvtv_plan_create(mvtv_plan **plan, const mvtv_plan_desc *desc);
+int mvtv_plan_destroy(mvtv_plan *plan);
+/* rows of D (inits.rowsD, cpp-code/solvers.cpp:38), vertices N, local slab [z0, z0+nz) of the last axis */
+int mvtv_plan_info(const mvtv_plan *plan, int64_t *N, int64_t *R, int64_t *z0, int64_t *nz);
+
+/* Replaces: nearest_interp_matrix + Ot*y + Ot*O (cpp-code/utils.cpp:311-352, solvers.cpp:32,37,40).
+ * Bins every point to its nearest vertex (ties -> lowest index), sorts by vertex and reduces segments
+ * (deterministic, increasing point index = arma's accumulation order).  With world>1 each rank passes
+ * exactly the points whose nearest vertex lies in its slab (multivartv_b200/partition.py buckets and
+ * exchanges them); a foreign point is MVTV_ERR_INVALID; mean(y) is all-reduced over the ranks. */
+int mvtv_plan_set_points(mvtv_plan *plan, int64_t n, const double *data_colmajor, const double *y,
+                         const double *axes);
+/* Same with inputs already resident in HBM (device pointers on the plan's device). */
+int mvtv_plan_set_points_dev(mvtv_plan *plan, int64_t n, const double *data_colmajor_dev,
+                             const double *y_dev, const double *axes_dev);
+/* Per-kernel-class CUDA-event timing on the plan's stream (used by bench.py for the roofline).
+ * ms[k], count[k], k = MVTV_KC_*: accumulated milliseconds and number of launches since enable. */
+#define MVTV_KC_ZU 0        /* fused z/u update + D^T products + norms */
+#define MVTV_KC_ZU_INIT 1   /* same kernel, initial D^T D theta / D^T u pass */
+#define MVTV_KC_CG_INIT 2   /* b, r = b - M theta, p */
+#define MVTV_KC_CG_SPMV 3   /* q = M p, p.q */
+#define MVTV_KC_CG_UPDATE 4 /* theta, r update, r.z, r.r */
+#define MVTV_KC_CG_DIR 5    /* p = z + beta p */
+#define MVTV_KC_N 8
+int mvtv_plan_profile(mvtv_plan *plan, int enable);
+int mvtv_plan_get_profile(mvtv_plan *plan, double *ms, int64_t *count);
+
+/* Debug / parity access to the cached operators: Oty (N), diag(crossO) (N), nearest vertex of each point (n) */
+int mvtv_plan_get_cache(mvtv_plan *plan, double *Oty, double *counts, int64_t *vertex_of_point);
+
+/* -- the hot path ---------------------------------------------------------------------------------
+ * Replaces: admm_update (cpp-code/solvers.hpp:85; rcpp solvers.hpp:100) and the solve+fitted part of
+ * mbs_one (cpp-code/solvers.hpp:89).  theta_init: N doubles or NULL (-> mean(y), cpp-code/solvers.cpp:94-99).
+ * u_inout: RCPP warm start in / final u out (R doubles, reference row order) or NULL (-> zeros in, nothing out).
+ * theta_out: N doubles.  fitted_out: n doubles (O*theta, cpp-code/solvers.cpp:66) or NULL.
+ * With world>1, theta_init/theta_out are the rank's LOCAL slab (nz*prod(m[0..p-2]) doubles) and u_inout must be NULL. */
+int mvtv_solve(mvtv_plan *plan, const mvtv_solve_params *prm, const double *theta_init, double *u_inout,
+               double *theta_out, double *fitted_out, mvtv_solve_result *res);
+
+/* Replaces: mbs_predict (cpp-code/solvers.hpp:93): nearest vertex of each new point, gather theta. */
+int mvtv_predict(mvtv_plan *plan, int64_t n_new, const double *data_colmajor, const double *axes,
+                 const double *theta, double *fits_out);
+
+/* -- operator-level entry points (parity tests, and drop-in for the reference's free functions) ---- */
+/* Replaces: D*theta and Dt*w (cpp-code/solvers.cpp:100,115,117-119) in the reference row order. */
+int mvtv_apply_D(mvtv_plan *plan, const double *theta, double *out_rows);
+int mvtv_apply_Dt(mvtv_plan *plan, const double *rows, double *out_vertices);
+/* Replaces: (crossO + s*crossD)*x (the system matrix of cpp-code/solvers.cpp:144) */
+int mvtv_apply_M(mvtv_plan *plan, double s, const double *x, double *out);
+/* Replaces: softthresh (cpp-code/solvers.hpp:22) */
+int mvtv_softthresh(int64_t n, const double *z, double lam, double *out);
+/* Replaces: nearest1 (cpp-code/utils.hpp:70) on a tensor-product mesh */
+int mvtv_nearest(int p, const int64_t *m, const double *axes, int64_t n, const double *data_colmajor,
+                 int64_t *vertex_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVTV_H */

@@ -1,0 +1,14 @@
+"""multivartv_b200 -- B200-native (sm_100a) implementation of the MultivarTV mesh-based ADMM hot path.
+
+The numerical work lives in ``lib/libmvtv_b200.so`` (hand-written CUDA behind the C ABI of
+``include/mvtv.h``); this package is the thin host-side mirror of the reference's solver interface.
+Importing the package does not load the library; the first call does, and fails loudly if it is missing.
+"""
+from . import _lib  # noqa: F401
+from ._lib import (F32, F64, MODE_CPP, MODE_PY, MODE_RCPP, PRECOND_JACOBI, VARIANT_INTENDED,  # noqa: F401
+                   VARIANT_REFERENCE, WARM_THETA_FROM_PLAN, WARM_U_FROM_PLAN, MvtvError, NotConverged)
+from .solvers import (Plan, axes_from_mesh, create_deltas, create_mesh, mbs_mse, mbs_one, mbs_predict,  # noqa: F401
+                      mesh_axes, mesh_from_axes, nccl_unique_id, nearest1, softthresh)
+
+__all__ = ["Plan", "mbs_one", "mbs_predict", "mbs_mse", "softthresh", "nearest1", "create_mesh", "mesh_axes",
+           "mesh_from_axes", "axes_from_mesh", "create_deltas", "MvtvError", "NotConverged"]

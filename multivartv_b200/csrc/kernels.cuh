@@ -1,0 +1,475 @@
+// Device code of the ADMM iteration (sm_100a).  All kernels are templates on the storage/arithmetic
+// type T (double | float); grid-wide reductions always accumulate in double.
+//
+// Kernel inventory (reference op each one replaces):
+//   k_zu        fused z/u update: D*theta - u -> softthresh -> u += r, D^T(alpha), D^T(u), D^T(u_old),
+//               ||r||^2 ||s||^2 ||D^T u||^2 ||D theta||^2 ||alpha||^2 max|dtheta|
+//               (cpp-code/solvers.cpp:115,117-120,113 ; rcpp solvers.cpp:112,114-117,119-122)
+//   k_cg_init   b = Oty + rho*D^T(alpha+u) (never stored), r = b - M theta, p = M_J^-1 r     (solvers.cpp:115-116)
+//   k_cg_spmv   q = (diag(c) + s*D^T D) p  as a 3^P-point clamped stencil, p.q                (solvers.cpp:116)
+//   k_cg_update theta += a p, r -= a q, r.z, r.r
+//   k_cg_dir    p = M_J^-1 r + beta p
+#pragma once
+#include "mvtv_internal.cuh"
+
+namespace mvtv {
+
+// slots of the ADMM reduction
+enum { ZR_R2 = 0, ZR_S2 = 1, ZR_DTU2 = 2, ZR_DTH2 = 3, ZR_AL2 = 4, ZR_DMAX = 5, ZR_N = 6, ZR_NSUM = 5 };
+
+// device scalars of the CG loop (doubles).  {r.z, r.r} live in two slots selected by the parity of
+// the number of iterations PERFORMED so far, so that once the done test fires every later launch sees
+// the same (frozen) state and returns immediately.
+enum {
+  CS_RZ0 = 0, CS_RR0 = 1, CS_RZ1 = 2, CS_RR1 = 3,
+  CS_BB = 4,     // b.b
+  CS_PQ = 5,     // p.q of the current iteration
+  CS_ITERS = 6,  // iterations performed
+  CS_N = 8
+};
+
+template <typename T>
+struct ZuArgs {
+  const T *theta;       // ghosted slab
+  const T *theta_prev;  // ghosted slab (theta before the x-update) or nullptr
+  const T *u_old;       // K blocks of usz
+  T *u_new;
+  T *v1, *v2;           // D^T alpha, D^T u_new (ghosted slab, owned part written)
+  double kappa;         // lambda / rho, may be +inf
+  double uscale;        // lazy rescale of adapt_step: true u_old = uscale * stored u_old
+  int mode;             // MVTV_MODE_*
+  int init;             // 1: alpha := D*theta, u unchanged (cpp-code/solvers.cpp:100-101), nothing written to u
+  double *red_out;      // ZR_N totals
+};
+
+template <typename T>
+__device__ __forceinline__ T soft_threshold(T z, T kappa) {
+  // cpp-code/solvers.cpp:24-29: sign(z) % max(|z| - kappa, 0)
+  T mag = fabs(z) - kappa;
+  mag = mag > T(0) ? mag : T(0);
+  T sg = (z > T(0)) ? T(1) : ((z < T(0)) ? T(-1) : T(0));
+  return sg * mag;
+}
+
+// Decode the in-plane coordinates of vertex q and return the two boundary bitmasks:
+// lo_ok bit a: i_a >= 1 ; hi_ok bit a: i_a <= m_a - 2.
+__device__ __forceinline__ void boundary_masks(const DimTab &dt, long long q, int zl, int &lo_ok, int &hi_ok) {
+  lo_ok = 0;
+  hi_ok = 0;
+  unsigned rem = (unsigned)q;
+  for (int a = 0; a < dt.P - 1; ++a) {
+    const unsigned ma = (unsigned)dt.m[a];
+    const unsigned ia = rem % ma;
+    rem /= ma;
+    lo_ok |= (ia >= 1u) << a;
+    hi_ok |= (ia + 2u <= ma) << a;
+  }
+  const long long gz = dt.z0 + zl;
+  lo_ok |= (gz >= 1) << (dt.P - 1);
+  hi_ok |= (gz + 2 <= dt.m[dt.P - 1]) << (dt.P - 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_zu (gather form).  One thread per vertex v of the slab (+ one plane of "ghost row" threads when a
+// lower neighbour rank exists).  For every block b and every subset e of its axis set the thread
+// re-derives the row owned by vertex v-e (D*theta from theta, u_old from memory), so the three
+// transposed products at v need no communication between threads; the thread whose e==0 owns the
+// row and is the only one that writes u_new and counts it in the norms.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_zu(const __grid_constant__ DimTab dt, const __grid_constant__ BlockTab bt, const ZuArgs<T> a,
+     const RedBuf rb) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int zl = (int)blockIdx.y - dt.has_lo;  // -1: ghost-row plane
+  double red[ZR_N] = {0, 0, 0, 0, 0, 0};
+  if (q < dt.plane) {
+    int lo_ok, hi_ok;
+    boundary_masks(dt, q, zl, lo_ok, hi_ok);
+    const long long base = (long long)(zl + 1) * dt.plane + q;
+    const bool owned = zl >= 0;
+    const int lastbit = 1 << (dt.P - 1);
+    const T kappa = (T)a.kappa;
+    const T usc = (T)a.uscale;
+    T acc1 = 0, acc2 = 0, acc3 = 0;
+    for (int b = 0; b < bt.K; ++b) {
+      const int S = bt.mask[b];
+      if (!owned && !(S & lastbit)) continue;
+      const int ns = bt.nsub[b];
+      const T sc = (T)bt.scale[b];
+      const T *uo_b = a.u_old + (size_t)b * dt.usz;
+      T *un_b = a.u_new + (size_t)b * dt.usz;
+      const int jmax = owned ? ns : 1;
+      for (int j = 0; j < jmax; ++j) {
+        const int e = bt.sub[b][j];
+        if ((e & ~lo_ok) != 0) continue;           // v-e leaves the mesh
+        if (((S & ~e) & ~hi_ok) != 0) continue;    // vertex v-e owns no row of this block
+        const long long w = base - bt.off[b][j];
+        T d = 0;
+        for (int f = 0; f < ns; ++f) {
+          const T t = a.theta[w + bt.off[b][f]];
+          d += (__popc(bt.sub[b][f]) & 1) ? -t : t;
+        }
+        d *= sc;
+        const T uo = usc * uo_b[w];
+        T al, un, pr;
+        if (a.init) {
+          al = d; un = uo; pr = 0;
+        } else {
+          al = soft_threshold<T>(d - uo, kappa);   // cpp :117
+          pr = al - d;                             // cpp :119
+          un = uo + pr;                            // cpp :120
+        }
+        const T sg = (__popc(e) & 1) ? -sc : sc;
+        acc1 += sg * al;
+        acc2 += sg * un;
+        acc3 += sg * uo;
+        if (j == 0) {
+          if (!a.init) un_b[w] = un;
+          if (owned) {
+            red[ZR_R2] += (double)pr * (double)pr;
+            red[ZR_DTH2] += (double)d * (double)d;
+            red[ZR_AL2] += (double)al * (double)al;
+          }
+        }
+      }
+    }
+    if (owned) {
+      a.v1[base] = acc1;
+      a.v2[base] = acc2;
+      // dual residual without its rho factor: cpp :118 D^T(alpha + u_old) ; rcpp :117 D^T(u_new - u_old)
+      const double sv = (a.mode == MVTV_MODE_RCPP) ? (double)acc2 - (double)acc3 : (double)acc1 + (double)acc3;
+      red[ZR_S2] = sv * sv;
+      red[ZR_DTU2] = (double)acc2 * (double)acc2;
+      if (a.theta_prev) red[ZR_DMAX] = fabs((double)a.theta[base] - (double)a.theta_prev[base]);
+    }
+  }
+  double *out = a.red_out;
+  grid_reduce<ZR_N, ZR_NSUM>(red, rb, [out](const double (&res)[ZR_N]) {
+#pragma unroll
+    for (int k = 0; k < ZR_N; ++k) out[k] = res[k];
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Clamped 3^P-point stencil, fully unrolled at compile time.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int A>
+struct StencilRec {
+  static __device__ __forceinline__ void run(const T *__restrict__ x, long long idx, int cidx,
+                                             const long long *om, const long long *op,
+                                             const StencilTab &st, T &acc) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const long long o = (d == 0) ? om[A] : ((d == 2) ? op[A] : 0);
+      StencilRec<T, A - 1>::run(x, idx + o, cidx * 3 + d, om, op, st, acc);
+    }
+  }
+};
+template <typename T>
+struct StencilRec<T, -1> {
+  static __device__ __forceinline__ void run(const T *__restrict__ x, long long idx, int cidx,
+                                             const long long *, const long long *, const StencilTab &st,
+                                             T &acc) {
+    acc += (T)st.coef[cidx] * x[idx];
+  }
+};
+
+// per-vertex neighbour offsets with Neumann clamping; returns the boundary class for diag(K)
+template <int P>
+__device__ __forceinline__ int neighbour_offsets(const DimTab &dt, long long q, int zl, long long (&om)[P],
+                                                 long long (&op)[P]) {
+  int cls = 0;
+  unsigned rem = (unsigned)q;
+#pragma unroll
+  for (int a = 0; a < P - 1; ++a) {
+    const unsigned ma = (unsigned)dt.m[a];
+    const unsigned ia = rem % ma;
+    rem /= ma;
+    om[a] = (ia >= 1u) ? -dt.stride[a] : 0;
+    op[a] = (ia + 2u <= ma) ? dt.stride[a] : 0;
+    cls |= ((ia == 0u) || (ia + 1u == ma)) << a;
+    // an axis of extent 1 has no neighbours at all: diag contribution handled by coef (L = 0)
+  }
+  const long long gz = dt.z0 + zl;
+  om[P - 1] = (gz >= 1) ? -dt.plane : 0;
+  op[P - 1] = (gz + 2 <= dt.m[P - 1]) ? dt.plane : 0;
+  cls |= ((gz == 0) || (gz + 1 == dt.m[P - 1])) << (P - 1);
+  return cls;
+}
+
+template <typename T>
+struct CgArgs {
+  T *x;          // theta (ghosted slab), updated in place
+  T *xold;       // copy of theta before the x-update (for max|dtheta|)
+  T *r, *p, *q;  // ghosted slabs
+  const T *c;    // diag(O^T O) = points per vertex
+  const T *oty, *v1, *v2;
+  double *S;     // CS_* scalars
+  double *raw;   // multi-GPU: reductions land here, are all-reduced, then committed by k_cg_commit_*;
+                 // nullptr on one GPU (the reducing kernel's last thread commits directly)
+  double rho;    // multiplies D^T(alpha+u) in b
+  double uscale; // lazy rescale of u: b = Oty + rho*(v1 + uscale*v2)
+  double rhoM;   // scalar of the system matrix diag(c) + rhoM * D^T D
+  double rtol2;  // cg_rtol^2
+};
+
+__device__ __forceinline__ bool cg_done(const double *S, double rtol2) {
+  const int cur = ((int)S[CS_ITERS]) & 1;
+  return S[2 * cur + 1] <= rtol2 * S[CS_BB];
+}
+__device__ __forceinline__ void cg_commit_init(double *S, const double *r3) {
+  S[CS_RZ0] = r3[0];
+  S[CS_RR0] = r3[1];
+  S[CS_BB] = r3[2];
+  S[CS_RZ1] = 0.0;
+  S[CS_RR1] = 0.0;
+  S[CS_PQ] = 1.0;
+  S[CS_ITERS] = 0.0;
+}
+__device__ __forceinline__ void cg_commit_update(double *S, const double *r2) {
+  const int nxt = (((int)S[CS_ITERS]) & 1) ^ 1;
+  S[2 * nxt] = r2[0];
+  S[2 * nxt + 1] = r2[1];
+  S[CS_ITERS] += 1.0;
+}
+
+template <typename T, int P>
+__global__ void __launch_bounds__(256)
+k_cg_init(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
+          const RedBuf rb) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int zl = blockIdx.y;
+  double red[3] = {0, 0, 0};
+  if (q < dt.plane) {
+    long long om[P], op[P];
+    const int cls = neighbour_offsets<P>(dt, q, zl, om, op);
+    const long long base = (long long)(zl + 1) * dt.plane + q;
+    T kx = 0;
+    StencilRec<T, P - 1>::run(a.x, base, 0, om, op, st, kx);
+    const T xv = a.x[base];
+    const T cv = a.c[base];
+    const T bv = a.oty[base] + (T)a.rho * (a.v1[base] + (T)a.uscale * a.v2[base]);
+    const T rv = bv - (cv * xv + (T)a.rhoM * kx);
+    const T dg = cv + (T)a.rhoM * (T)st.diagK[cls];
+    const T zv = rv / dg;
+    a.r[base] = rv;
+    a.p[base] = zv;
+    a.xold[base] = xv;
+    red[0] = (double)rv * (double)zv;
+    red[1] = (double)rv * (double)rv;
+    red[2] = (double)bv * (double)bv;
+  }
+  double *S = a.S, *raw = a.raw;
+  grid_reduce<3, 3>(red, rb, [S, raw](const double (&res)[3]) {
+    if (raw) { raw[0] = res[0]; raw[1] = res[1]; raw[2] = res[2]; }
+    else cg_commit_init(S, res);
+  });
+}
+
+template <typename T, int P>
+__global__ void __launch_bounds__(256)
+k_cg_spmv(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
+          const RedBuf rb) {
+  if (cg_done(a.S, a.rtol2)) return;
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int zl = blockIdx.y;
+  double red[1] = {0};
+  if (q < dt.plane) {
+    long long om[P], op[P];
+    neighbour_offsets<P>(dt, q, zl, om, op);
+    const long long base = (long long)(zl + 1) * dt.plane + q;
+    T kp = 0;
+    StencilRec<T, P - 1>::run(a.p, base, 0, om, op, st, kp);
+    const T pv = a.p[base];
+    const T qv = a.c[base] * pv + (T)a.rhoM * kp;
+    a.q[base] = qv;
+    red[0] = (double)pv * (double)qv;
+  }
+  double *dst = a.raw ? a.raw : (a.S + CS_PQ);
+  grid_reduce<1, 1>(red, rb, [dst](const double (&res)[1]) { dst[0] = res[0]; });
+}
+
+// plain M*x for the ABI-level mvtv_apply_M
+template <typename T, int P>
+__global__ void __launch_bounds__(256)
+k_apply_M(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const T *x, const T *c,
+          double s, T *out) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int zl = blockIdx.y;
+  if (q < dt.plane) {
+    long long om[P], op[P];
+    neighbour_offsets<P>(dt, q, zl, om, op);
+    const long long base = (long long)(zl + 1) * dt.plane + q;
+    T kx = 0;
+    StencilRec<T, P - 1>::run(x, base, 0, om, op, st, kx);
+    out[base] = c[base] * x[base] + (T)s * kx;
+  }
+}
+
+template <typename T, int P>
+__global__ void __launch_bounds__(256)
+k_cg_update(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
+            const RedBuf rb) {
+  if (cg_done(a.S, a.rtol2)) return;
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int zl = blockIdx.y;
+  double red[2] = {0, 0};
+  const int cur = ((int)a.S[CS_ITERS]) & 1;
+  const T alpha = (T)(a.S[2 * cur] / a.S[CS_PQ]);
+  if (q < dt.plane) {
+    long long om[P], op[P];
+    const int cls = neighbour_offsets<P>(dt, q, zl, om, op);
+    const long long base = (long long)(zl + 1) * dt.plane + q;
+    const T pv = a.p[base];
+    const T rv = a.r[base] - alpha * a.q[base];
+    a.x[base] += alpha * pv;
+    a.r[base] = rv;
+    const T dg = a.c[base] + (T)a.rhoM * (T)st.diagK[cls];
+    red[0] = (double)rv * (double)(rv / dg);
+    red[1] = (double)rv * (double)rv;
+  }
+  double *S = a.S, *raw = a.raw;
+  grid_reduce<2, 2>(red, rb, [S, raw](const double (&res)[2]) {
+    if (raw) { raw[0] = res[0]; raw[1] = res[1]; }
+    else cg_commit_update(S, res);
+  });
+}
+
+template <typename T, int P>
+__global__ void __launch_bounds__(256)
+k_cg_dir(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a) {
+  if (cg_done(a.S, a.rtol2)) return;  // also true right after the update that converged
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int zl = blockIdx.y;
+  const int n = ((int)a.S[CS_ITERS]) & 1;
+  const T beta = (T)(a.S[2 * n] / a.S[2 * (n ^ 1)]);
+  if (q < dt.plane) {
+    long long om[P], op[P];
+    const int cls = neighbour_offsets<P>(dt, q, zl, om, op);
+    const long long base = (long long)(zl + 1) * dt.plane + q;
+    const T dg = a.c[base] + (T)a.rhoM * (T)st.diagK[cls];
+    a.p[base] = a.r[base] / dg + beta * a.p[base];
+  }
+}
+
+// multi-GPU commits (after the all-reduce of `raw`)
+__global__ void k_cg_commit_init(double *S, const double *raw) { cg_commit_init(S, raw); }
+__global__ void k_cg_commit_pq(double *S, const double *raw, double rtol2) {
+  if (cg_done(S, rtol2)) return;
+  S[CS_PQ] = raw[0];
+}
+__global__ void k_cg_commit_update(double *S, const double *raw, double rtol2) {
+  if (cg_done(S, rtol2)) return;
+  cg_commit_update(S, raw);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_fill(T *x, long long n, T v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = v;
+}
+template <typename T>
+__global__ void k_scale(T *x, long long n, T s) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] *= s;
+}
+// dst (ghosted slab, type T) <- src (contiguous owned part, double) and back
+template <typename T>
+__global__ void k_import(T *dst_ghosted, const double *src, long long plane, long long nloc) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (long long)gridDim.x * blockDim.x)
+    dst_ghosted[i + plane] = (T)src[i];
+}
+template <typename T>
+__global__ void k_export(double *dst, const T *src_ghosted, long long plane, long long nloc) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (double)src_ghosted[i + plane];
+}
+__global__ void k_softthresh(const double *z, double lam, double *out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = soft_threshold<double>(z[i], lam);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ABI-boundary kernels in the reference's compact row layout (single GPU only)
+// ---------------------------------------------------------------------------------------------
+// direction 0: padded u (type T, times uscale) -> compact rows (double) ; 1: compact -> padded
+template <typename T>
+__global__ void k_u_convert(const __grid_constant__ DimTab dt, const __grid_constant__ RowTab rt, T *u_padded,
+                            double *rows, double uscale, int direction) {
+  const int b = blockIdx.y;
+  const long long nrow = rt.rows[b];
+  const int S = rt.mask[b];
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += (long long)gridDim.x * blockDim.x) {
+    long long rem = r, v = 0;
+    for (int a = 0; a < dt.P; ++a) {
+      const long long rd = dt.m[a] - ((S >> a) & 1);
+      v += (rem % rd) * dt.stride[a];
+      rem /= rd;
+    }
+    const size_t pi = (size_t)b * dt.usz + dt.plane + v;
+    if (direction == 0) rows[rt.row_off[b] + r] = uscale * (double)u_padded[pi];
+    else u_padded[pi] = (T)rows[rt.row_off[b] + r];
+  }
+}
+
+// out_rows = D * theta  (compact layout, double in/out; theta ghosted slab of doubles)
+__global__ void k_apply_D(const __grid_constant__ DimTab dt, const __grid_constant__ BlockTab bt,
+                          const __grid_constant__ RowTab rt, const double *theta_ghosted, double *rows) {
+  const int b = blockIdx.y;
+  const long long nrow = rt.rows[b];
+  const int S = rt.mask[b];
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += (long long)gridDim.x * blockDim.x) {
+    long long rem = r, v = 0;
+    for (int a = 0; a < dt.P; ++a) {
+      const long long rd = dt.m[a] - ((S >> a) & 1);
+      v += (rem % rd) * dt.stride[a];
+      rem /= rd;
+    }
+    const long long base = dt.plane + v;
+    double d = 0;
+    for (int f = 0; f < bt.nsub[b]; ++f) {
+      const double t = theta_ghosted[base + bt.off[b][f]];
+      d += (__popc(bt.sub[b][f]) & 1) ? -t : t;
+    }
+    rows[rt.row_off[b] + r] = bt.scale[b] * d;
+  }
+}
+
+// out = D^T * rows  (rows compact, out ghosted slab of doubles)
+__global__ void k_apply_Dt(const __grid_constant__ DimTab dt, const __grid_constant__ BlockTab bt,
+                           const __grid_constant__ RowTab rt, const double *rows, double *out_ghosted) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int zl = blockIdx.y;
+  if (q >= dt.plane) return;
+  int lo_ok, hi_ok;
+  boundary_masks(dt, q, zl, lo_ok, hi_ok);
+  // coordinates again, for the compact row index
+  long long idx[MVTV_MAXP];
+  {
+    long long rem = q;
+    for (int a = 0; a < dt.P - 1; ++a) { idx[a] = rem % dt.m[a]; rem /= dt.m[a]; }
+    idx[dt.P - 1] = zl;
+  }
+  double total = 0;
+  for (int b = 0; b < bt.K; ++b) {
+    const int S = bt.mask[b];
+    double acc = 0;
+    for (int j = 0; j < bt.nsub[b]; ++j) {
+      const int e = bt.sub[b][j];
+      if ((e & ~lo_ok) != 0) continue;
+      if (((S & ~e) & ~hi_ok) != 0) continue;
+      long long r = 0;
+      for (int a = 0; a < dt.P; ++a) r += (idx[a] - ((e >> a) & 1)) * rt.rstride[b][a];
+      const double w = rows[rt.row_off[b] + r];
+      acc += (__popc(e) & 1) ? -w : w;
+    }
+    total += bt.scale[b] * acc;
+  }
+  out_ghosted[(long long)(zl + 1) * dt.plane + q] = total;
+}
+
+}  // namespace mvtv

@@ -1,0 +1,1085 @@
+// Host driver + C ABI of libmvtv_b200.so: plan construction (block table of D, stencil of D^T D),
+// the ADMM loop of admm_update (cpp-code/solvers.cpp:90-130, rcpp solvers.cpp:96-136,
+// code/solvers.py:54-76) and the matrix-free PCG that replaces arma::spsolve (cpp-code/solvers.cpp:116).
+// There is no CPU fallback anywhere in this file: without a usable CUDA device every entry point fails.
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+#include "kernels.cuh"
+#include "setup.h"
+
+namespace mvtv {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (torch's bundled libnccl.so.2 is already mapped when the caller is a
+// torch.distributed process; the single-GPU path never touches NCCL)
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+
+  void load() {
+    if (handle) return;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+      handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) throw Error(MVTV_ERR_CUDA, std::string("dlopen(libnccl.so.2) failed: ") + dlerror());
+#define MVTV_SYM(field, name)                                                       \
+  field = reinterpret_cast<decltype(field)>(dlsym(handle, name));                   \
+  if (!field) throw Error(MVTV_ERR_CUDA, std::string("NCCL symbol missing: ") + name)
+    MVTV_SYM(CommInitRank, "ncclCommInitRank");
+    MVTV_SYM(CommDestroy, "ncclCommDestroy");
+    MVTV_SYM(GetUniqueId, "ncclGetUniqueId");
+    MVTV_SYM(AllReduce, "ncclAllReduce");
+    MVTV_SYM(Send, "ncclSend");
+    MVTV_SYM(Recv, "ncclRecv");
+    MVTV_SYM(GroupStart, "ncclGroupStart");
+    MVTV_SYM(GroupEnd, "ncclGroupEnd");
+    MVTV_SYM(GetErrorString, "ncclGetErrorString");
+#undef MVTV_SYM
+  }
+};
+static NcclApi g_nccl;
+
+#define MVTV_NCCL(expr)                                                                             \
+  do {                                                                                              \
+    ncclResult_t _r = (expr);                                                                       \
+    if (_r != ncclSuccess)                                                                          \
+      throw ::mvtv::Error(MVTV_ERR_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(_r));    \
+  } while (0)
+
+static inline int pdep_int(int j, int S) {
+  int e = 0, k = 0;
+  for (int a = 0; a < 8; ++a)
+    if ((S >> a) & 1) {
+      if ((j >> k) & 1) e |= 1 << a;
+      ++k;
+    }
+  return e;
+}
+
+template <typename T> struct NcclType;
+template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclFloat64; };
+template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat32; };
+
+}  // namespace mvtv
+
+using namespace mvtv;
+
+// ------------------------------------------------------------------------------------------------
+struct mvtv_plan {
+  int p = 0;            // user-visible number of axes
+  int dtype = MVTV_F64;
+  int variant = 0;
+  int device = 0;
+  int rank = 0, world = 1;
+  DimTab dt{};
+  BlockTab bt{};
+  RowTab rt{};
+  StencilTab st{};
+  long long N = 0;      // global vertices
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ncclComm_t comm = nullptr;
+
+  // device state (element type = dtype)
+  void *theta = nullptr, *xold = nullptr, *v1 = nullptr, *v2 = nullptr, *oty = nullptr, *cnt = nullptr;
+  void *r = nullptr, *pvec = nullptr, *q = nullptr;
+  void *u[2] = {nullptr, nullptr};
+  int ucur = 0;
+  double uscale = 1.0;
+  double rho_state = 0.0;
+  bool have_u_state = false, have_theta_state = false;
+
+  double *S = nullptr, *zr = nullptr, *raw = nullptr;   // device scalars
+  double *partials = nullptr;
+  unsigned *counters = nullptr;  // [0] zu, [1] cg_init, [2] spmv, [3] update, [4] misc
+  double *h_scal = nullptr;      // pinned host mirror (16 doubles)
+  dim3 grid, block;
+  unsigned nblocks = 0;
+
+  // points
+  long long n = 0;
+  long long *vid = nullptr;
+  double mean_y = 0.0;
+  bool have_points = false;
+
+  double *staging = nullptr;
+  size_t staging_bytes = 0;
+  long long launches = 0;
+  int last_cg_iters = 8;
+
+  // optional per-kernel-class CUDA-event timing on the plan's stream (mvtv_plan_profile)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  struct ProfRec { int cls, e0; };
+  std::vector<ProfRec> prof_recs;
+  size_t prof_used = 0;
+  double prof_ms[MVTV_KC_N] = {0};
+  long long prof_cnt[MVTV_KC_N] = {0};
+  void prof_begin(int cls) {
+    if (!prof_on) return;
+    while (prof_ev.size() < prof_used + 2) {
+      cudaEvent_t e;
+      MVTV_CUDA(cudaEventCreate(&e));
+      prof_ev.push_back(e);
+    }
+    MVTV_CUDA(cudaEventRecord(prof_ev[prof_used], stream));
+    prof_recs.push_back({cls, (int)prof_used});
+  }
+  void prof_end() {
+    if (!prof_on) return;
+    MVTV_CUDA(cudaEventRecord(prof_ev[prof_used + 1], stream));
+    prof_used += 2;
+  }
+  void prof_flush() {  // call only after a stream synchronize
+    if (!prof_on) return;
+    for (const ProfRec &r : prof_recs) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, prof_ev[r.e0], prof_ev[r.e0 + 1]) == cudaSuccess) {
+        prof_ms[r.cls] += ms;
+        prof_cnt[r.cls] += 1;
+      }
+    }
+    prof_recs.clear();
+    prof_used = 0;
+  }
+
+  size_t esz() const { return dtype == MVTV_F64 ? 8 : 4; }
+
+  void use_device() const { MVTV_CUDA(cudaSetDevice(device)); }
+
+  double *stage(size_t bytes) {
+    if (bytes > staging_bytes) {
+      if (staging) MVTV_CUDA(cudaFree(staging));
+      staging = nullptr;
+      staging_bytes = 0;
+      MVTV_CUDA(cudaMalloc(&staging, bytes));
+      staging_bytes = bytes;
+    }
+    return staging;
+  }
+
+  ~mvtv_plan() {
+    cudaSetDevice(device);
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pvec, q, u[0], u[1], S, zr, raw, partials, counters, vid, staging};
+    for (void *b : bufs)
+      if (b) cudaFree(b);
+    if (h_scal) cudaFreeHost(h_scal);
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  // ---- construction ---------------------------------------------------------------------------
+  void build_tables(const mvtv_plan_desc &d) {
+    p = d.p;
+    const int P = p < 2 ? 2 : p;  // a 1-D mesh is stored as (m, 1)
+    long long m[MVTV_MAXP];
+    for (int a = 0; a < P; ++a) m[a] = a < p ? d.m[a] : 1;
+    for (int a = 0; a < p; ++a) MVTV_REQUIRE(m[a] >= 1, "mesh dims must be >= 1");
+    N = 1;
+    for (int a = 0; a < P; ++a) N *= m[a];
+    MVTV_REQUIRE(N < (1ll << 31), "mesh too large for 32-bit in-slab vertex keys");
+    dt.P = P;
+    long long s = 1;
+    for (int a = 0; a < MVTV_MAXP; ++a) {
+      dt.m[a] = a < P ? m[a] : 1;
+      dt.stride[a] = a < P ? s : 0;
+      if (a < P) s *= m[a];
+    }
+    dt.plane = dt.stride[P - 1];
+    // slab partition of the last axis: contiguous, sizes differ by at most one plane
+    const long long mz = m[P - 1];
+    if (world > 1) {
+      if (p < 2) throw Error(MVTV_ERR_UNSUPPORTED, "slab partitioning needs p >= 2");
+      if (mz < world) throw Error(MVTV_ERR_INVALID, "last mesh axis shorter than the number of ranks");
+    }
+    const long long basez = mz / world, extra = mz % world;
+    dt.z0 = rank * basez + std::min<long long>(rank, extra);
+    dt.nz = (int)(basez + (rank < extra ? 1 : 0));
+    dt.has_lo = rank > 0;
+    dt.has_hi = rank < world - 1;
+    dt.Nloc = dt.plane * dt.nz;
+    dt.usz = dt.plane * (dt.nz + 2);
+
+    // difference blocks in create_D order (cpp-code/utils.cpp:245-269)
+    const int K = (1 << p) - 1;
+    bt.K = K;
+    rt.K = K;
+    long long off = 0;
+    for (int b = 0; b < K; ++b) {
+      const int num = (b == 0) ? K : b;  // all-ones mask first (:258), then binaries of 1..K-1 (:259-267)
+      int Sm = 0;                        // MSB-first binaries (:73-89): axis a <-> bit p-1-a
+      for (int a = 0; a < p; ++a)
+        if ((num >> (p - 1 - a)) & 1) Sm |= 1 << a;
+      double sc = 1.0;                   // prod_{k not in S} delta_k (:261); all-ones block unscaled
+      if (b != 0 && d.deltas)
+        for (int a = 0; a < p; ++a)
+          if (!((Sm >> a) & 1)) sc *= d.deltas[a];
+      int Sp = Sm;
+      if (__builtin_popcount(Sm) > 1 && variant == MVTV_VARIANT_REFERENCE) {
+        const int lowest = __builtin_ctz(Sm);
+        Sp = (Sm & ~(1 << lowest)) | 1;  // first factor along axis 0 (cpp-code/utils.cpp:187)
+        if (lowest != 0 && m[0] != m[lowest])
+          throw Error(MVTV_ERR_DIM_MISMATCH,
+                      "matrix multiplication: incompatible matrix dimensions (reference mixedpartial on a "
+                      "non-cubic mesh, cpp-code/utils.cpp:187,216); use MVTV_VARIANT_INTENDED");
+      }
+      bt.mask[b] = Sp;
+      bt.scale[b] = sc;
+      bt.nsub[b] = 1 << __builtin_popcount(Sp);
+      for (int j = 0; j < bt.nsub[b]; ++j) {
+        const int e = pdep_int(j, Sp);
+        bt.sub[b][j] = e;
+        long long o = 0;
+        for (int a = 0; a < P; ++a)
+          if ((e >> a) & 1) o += dt.stride[a];
+        bt.off[b][j] = o;
+      }
+      rt.mask[b] = Sp;
+      long long rs = 1;
+      for (int a = 0; a < MVTV_MAXP; ++a) {
+        rt.rstride[b][a] = a < P ? rs : 0;
+        if (a < P) rs *= m[a] - ((Sp >> a) & 1);
+      }
+      rt.rows[b] = rs;
+      rt.row_off[b] = off;
+      off += rs;
+    }
+    rt.R = off;
+
+    // 3^P-point stencil of D^T D = sum_b c_b^2 kron_{a in S'_b} L_a  (SURVEY A.6), clamped indices
+    st.npts = 1;
+    for (int a = 0; a < P; ++a) st.npts *= 3;
+    const double t3[3] = {-1.0, 2.0, -1.0};
+    for (int o = 0; o < st.npts; ++o) {
+      double c = 0.0;
+      for (int b = 0; b < K; ++b) {
+        double w = bt.scale[b] * bt.scale[b];
+        int rem = o;
+        for (int a = 0; a < P; ++a) {
+          const int dgt = rem % 3;
+          rem /= 3;
+          if ((bt.mask[b] >> a) & 1) w *= t3[dgt];
+          else w *= (dgt == 1) ? 1.0 : 0.0;
+        }
+        c += w;
+      }
+      st.coef[o] = c;
+    }
+    for (int cls = 0; cls < (1 << P); ++cls) {
+      double dsum = 0.0;
+      for (int b = 0; b < K; ++b) {
+        double w = bt.scale[b] * bt.scale[b];
+        for (int a = 0; a < P; ++a)
+          if ((bt.mask[b] >> a) & 1) {
+            const bool bnd = (cls >> a) & 1;
+            w *= bnd ? (m[a] >= 2 ? 1.0 : 0.0) : 2.0;
+          }
+        dsum += w;
+      }
+      st.diagK[cls] = dsum;
+    }
+  }
+
+  void allocate() {
+    use_device();
+    MVTV_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    MVTV_CUDA(cudaEventCreate(&ev0));
+    MVTV_CUDA(cudaEventCreate(&ev1));
+    const size_t vb = (size_t)dt.usz * esz();
+    void **vecs[] = {&theta, &xold, &v1, &v2, &oty, &cnt, &r, &pvec, &q};
+    for (void **v : vecs) {
+      MVTV_CUDA(cudaMalloc(v, vb));
+      MVTV_CUDA(cudaMemsetAsync(*v, 0, vb, stream));
+    }
+    for (int k = 0; k < 2; ++k) {
+      MVTV_CUDA(cudaMalloc(&u[k], vb * bt.K));
+      MVTV_CUDA(cudaMemsetAsync(u[k], 0, vb * bt.K, stream));
+    }
+    block = dim3(256, 1, 1);
+    grid = dim3((unsigned)((dt.plane + 255) / 256), (unsigned)(dt.nz + dt.has_lo), 1);
+    MVTV_REQUIRE(grid.y <= 65535, "last mesh axis too long for grid.y");
+    nblocks = grid.x * grid.y;
+    MVTV_CUDA(cudaMalloc(&partials, sizeof(double) * (size_t)nblocks * ZR_N));
+    MVTV_CUDA(cudaMalloc(&counters, sizeof(unsigned) * 8));
+    MVTV_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned) * 8, stream));
+    MVTV_CUDA(cudaMalloc(&S, sizeof(double) * CS_N));
+    MVTV_CUDA(cudaMalloc(&zr, sizeof(double) * 8));
+    MVTV_CUDA(cudaMalloc(&raw, sizeof(double) * 8));
+    MVTV_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * CS_N, stream));
+    MVTV_CUDA(cudaMemsetAsync(zr, 0, sizeof(double) * 8, stream));
+    MVTV_CUDA(cudaMemsetAsync(raw, 0, sizeof(double) * 8, stream));
+    MVTV_CUDA(cudaMallocHost(&h_scal, sizeof(double) * 16));
+    MVTV_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  dim3 grid_owned() const { return dim3(grid.x, (unsigned)dt.nz, 1); }
+  static int grid1d(long long n) {
+    long long g = (n + 255) / 256;
+    return (int)std::max<long long>(1, std::min<long long>(g, 148 * 16));
+  }
+
+  // ---- multi-GPU plumbing --------------------------------------------------------------------
+  template <typename T>
+  void exchange_ghosts(T *x) {
+    if (world == 1) return;
+    const size_t pl = (size_t)dt.plane;
+    MVTV_NCCL(g_nccl.GroupStart());
+    if (dt.has_hi) {
+      MVTV_NCCL(g_nccl.Send(x + (size_t)dt.nz * pl, pl, NcclType<T>::v, rank + 1, comm, stream));
+      MVTV_NCCL(g_nccl.Recv(x + (size_t)(dt.nz + 1) * pl, pl, NcclType<T>::v, rank + 1, comm, stream));
+    }
+    if (dt.has_lo) {
+      MVTV_NCCL(g_nccl.Send(x + pl, pl, NcclType<T>::v, rank - 1, comm, stream));
+      MVTV_NCCL(g_nccl.Recv(x, pl, NcclType<T>::v, rank - 1, comm, stream));
+    }
+    MVTV_NCCL(g_nccl.GroupEnd());
+  }
+  void allreduce(double *buf, int n, ncclRedOp_t op) {
+    if (world == 1) return;
+    MVTV_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat64, op, comm, stream));
+  }
+
+  // ---- points --------------------------------------------------------------------------------
+  template <typename T>
+  void set_points_t(long long npts, const double *data_dev, const double *y_dev, const double *axes_dev) {
+    use_device();
+    MVTV_REQUIRE(npts >= 1 && npts < (1ll << 31), "n must be in [1, 2^31)");
+    if (vid) MVTV_CUDA(cudaFree(vid));
+    vid = nullptr;
+    MVTV_CUDA(cudaMalloc(&vid, sizeof(long long) * (size_t)npts));
+    unsigned *key_in, *key_out, *val_in, *val_out;
+    void *temp;
+    const size_t tb = sort_temp_bytes(npts);
+    MVTV_CUDA(cudaMalloc(&key_in, sizeof(unsigned) * (size_t)npts * 4));
+    key_out = key_in + npts;
+    val_in = key_out + npts;
+    val_out = val_in + npts;
+    MVTV_CUDA(cudaMalloc(&temp, std::max<size_t>(tb, 16)));
+    try {
+      launch_bin(p, dt, npts, data_dev, axes_dev, vid, key_in, val_in, stream);
+      launch_sort(temp, tb, npts, key_in, key_out, val_in, val_out, stream);
+      const size_t vb = (size_t)dt.usz * esz();
+      MVTV_CUDA(cudaMemsetAsync(oty, 0, vb, stream));
+      MVTV_CUDA(cudaMemsetAsync(cnt, 0, vb, stream));
+      launch_segment_reduce<T>(npts, key_out, val_out, y_dev, dt.plane, (T *)oty, (T *)cnt, stream);
+      launches += 5;
+      // mean(y) (cpp-code/solvers.cpp:95,103): deterministic two-level sum on the device
+      sum_y(y_dev, npts);
+      MVTV_CUDA(cudaStreamSynchronize(stream));
+      if (world > 1) {
+        // every rank must hold exactly the points of its own slab (partition.exchange_points)
+        unsigned last_key = 0;
+        MVTV_CUDA(cudaMemcpy(&last_key, key_out + (npts - 1), sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (last_key == 0xFFFFFFFFu)
+          throw Error(MVTV_ERR_INVALID, "world > 1: a point's nearest vertex lies outside this rank's slab");
+      }
+    } catch (...) {
+      cudaFree(key_in);
+      cudaFree(temp);
+      throw;
+    }
+    MVTV_CUDA(cudaFree(key_in));
+    MVTV_CUDA(cudaFree(temp));
+    n = npts;
+    have_points = true;
+    have_u_state = have_theta_state = false;
+  }
+  void sum_y(const double *y_dev, long long npts);
+
+  // ---- the ADMM loop ---------------------------------------------------------------------------
+  template <typename T, int P>
+  int cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, long long &inner, int &status);
+  template <typename T>
+  void launch_zu(double kappa, double usc, int mode, int init, bool with_prev);
+  template <typename T>
+  int solve_t(const mvtv_solve_params &prm, const double *theta_init, double *u_inout, double *theta_out,
+              double *fitted_out, mvtv_solve_result &res);
+  template <typename T>
+  void read_scalars(const double *dev, int count) {
+    MVTV_CUDA(cudaMemcpyAsync(h_scal, dev, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
+    MVTV_CUDA(cudaStreamSynchronize(stream));
+    prof_flush();
+  }
+};
+
+// sum of y with the deterministic grid reduction
+__global__ void __launch_bounds__(256) k_sum(const double *__restrict__ y, long long n, RedBuf rb, double *out) {
+  double red[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    red[0] += y[i];
+  grid_reduce<1, 1>(red, rb, [out](const double (&res)[1]) { out[0] = res[0]; });
+}
+// max |x - c| over the owned slab (the first CPP/PY loop test against thetaold = mean(y)-0.1, cpp :103-104,113)
+template <typename T>
+__global__ void __launch_bounds__(256) k_maxabs_const(const T *__restrict__ x_ghosted, long long plane, long long nloc,
+                                                      double c, RedBuf rb, double *out) {
+  double red[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (long long)gridDim.x * blockDim.x)
+    red[0] = fmax(red[0], fabs((double)x_ghosted[plane + i] - c));
+  grid_reduce<1, 0>(red, rb, [out](const double (&res)[1]) { out[0] = res[0]; });
+}
+
+void mvtv_plan::sum_y(const double *y_dev, long long npts) {
+  const int g = std::min<int>(grid1d(npts), (int)nblocks);
+  RedBuf rb{partials, counters + 4};
+  k_sum<<<g, 256, 0, stream>>>(y_dev, npts, rb, zr);
+  MVTV_CUDA(cudaGetLastError());
+  launches += 1;
+  double cnt_total = (double)npts;
+  if (world > 1) {  // global mean over the disjoint per-rank point sets
+    MVTV_CUDA(cudaMemcpyAsync(zr + 1, &cnt_total, sizeof(double), cudaMemcpyHostToDevice, stream));
+    allreduce(zr, 2, ncclSum);
+  }
+  MVTV_CUDA(cudaMemcpyAsync(h_scal, zr, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream));
+  MVTV_CUDA(cudaStreamSynchronize(stream));
+  if (world > 1) cnt_total = h_scal[1];
+  mean_y = h_scal[0] / cnt_total;
+}
+
+template <typename T>
+void mvtv_plan::launch_zu(double kappa, double usc, int mode, int init, bool with_prev) {
+  ZuArgs<T> a;
+  a.theta = (const T *)theta;
+  a.theta_prev = with_prev ? (const T *)xold : nullptr;
+  a.u_old = (const T *)u[ucur];
+  a.u_new = (T *)u[ucur ^ 1];
+  a.v1 = (T *)v1;
+  a.v2 = (T *)v2;
+  a.kappa = kappa;
+  a.uscale = usc;
+  a.mode = mode;
+  a.init = init;
+  a.red_out = zr;
+  RedBuf rb{partials, counters + 0};
+  prof_begin(init ? MVTV_KC_ZU_INIT : MVTV_KC_ZU);
+  k_zu<T><<<grid, block, 0, stream>>>(dt, bt, a, rb);
+  prof_end();
+  MVTV_CUDA(cudaGetLastError());
+  launches += 1;
+  if (world > 1) {
+    allreduce(zr, ZR_NSUM, ncclSum);
+    allreduce(zr + ZR_NSUM, ZR_N - ZR_NSUM, ncclMax);
+  }
+}
+
+template <typename T, int P>
+int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, long long &inner, int &status) {
+  CgArgs<T> a;
+  a.x = (T *)theta;
+  a.xold = (T *)xold;
+  a.r = (T *)r;
+  a.p = (T *)pvec;
+  a.q = (T *)q;
+  a.c = (const T *)cnt;
+  a.oty = (const T *)oty;
+  a.v1 = (const T *)v1;
+  a.v2 = (const T *)v2;
+  a.S = S;
+  a.raw = world > 1 ? raw : nullptr;
+  a.rho = rho;
+  a.uscale = usc;
+  a.rhoM = rhoM;
+  a.rtol2 = rtol * rtol;
+  const dim3 g = grid_owned();
+  const unsigned nb = g.x * g.y;
+  (void)nb;
+  prof_begin(MVTV_KC_CG_INIT);
+  k_cg_init<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1});
+  prof_end();
+  MVTV_CUDA(cudaGetLastError());
+  launches += 1;
+  if (world > 1) {
+    allreduce(raw, 3, ncclSum);
+    k_cg_commit_init<<<1, 1, 0, stream>>>(S, raw);
+    launches += 1;
+  }
+  int launched = 0;
+  int batch = std::max(2, std::min(last_cg_iters, 256));
+  double iters = 0;
+  for (;;) {
+    for (int k = 0; k < batch; ++k) {
+      if (world > 1) exchange_ghosts<T>((T *)pvec);
+      prof_begin(MVTV_KC_CG_SPMV);
+      k_cg_spmv<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2});
+      prof_end();
+      if (world > 1) {
+        allreduce(raw, 1, ncclSum);
+        k_cg_commit_pq<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
+      }
+      prof_begin(MVTV_KC_CG_UPDATE);
+      k_cg_update<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 3});
+      prof_end();
+      if (world > 1) {
+        allreduce(raw, 2, ncclSum);
+        k_cg_commit_update<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
+      }
+      prof_begin(MVTV_KC_CG_DIR);
+      k_cg_dir<T, P><<<g, block, 0, stream>>>(dt, st, a);
+      prof_end();
+      launches += world > 1 ? 5 : 3;
+    }
+    MVTV_CUDA(cudaGetLastError());
+    launched += batch;
+    read_scalars<T>(S, CS_N);
+    iters = h_scal[CS_ITERS];
+    const int cur = ((int)iters) & 1;
+    const bool done = h_scal[2 * cur + 1] <= a.rtol2 * h_scal[CS_BB];
+    if (done) break;
+    if (!(h_scal[CS_BB] == h_scal[CS_BB]) || !(h_scal[2 * cur + 1] == h_scal[2 * cur + 1])) {
+      status = MVTV_ERR_INNER_SOLVE;  // NaN
+      break;
+    }
+    if (launched >= maxit) {
+      // fp64: a real failure.  fp32: the recursive residual can stagnate above cg_rtol; accept theta.
+      if (sizeof(T) == 8) status = MVTV_ERR_INNER_SOLVE;
+      break;
+    }
+    batch = std::max(2, std::min({batch, 64, maxit - launched}));
+  }
+  inner += (long long)iters;
+  last_cg_iters = (int)iters + 1;
+  return (int)iters;
+}
+
+template <typename T>
+int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, double *u_inout,
+                       double *theta_out, double *fitted_out, mvtv_solve_result &res) {
+  use_device();
+  MVTV_REQUIRE(have_points, "mvtv_solve: call mvtv_plan_set_points first");
+  const int mode = prm.mode;
+  MVTV_REQUIRE(mode == MVTV_MODE_CPP || mode == MVTV_MODE_RCPP || mode == MVTV_MODE_PY, "bad mode");
+  const double lambda = prm.lambda;
+  MVTV_REQUIRE(lambda > 0.0, "lambda must be > 0");
+  MVTV_REQUIRE(!(world > 1 && u_inout), "u_inout is not supported with world > 1 (use MVTV_WARM_U_FROM_PLAN)");
+  const double tol = (prm.tol > 0.0) ? prm.tol : (mode == MVTV_MODE_RCPP ? 1e-4 : 1e-3);
+  const int max_counter = prm.max_counter > 0 ? prm.max_counter
+                          : (mode == MVTV_MODE_CPP ? 2000 : (mode == MVTV_MODE_RCPP ? 3000 : 5000));
+  const double cg_rtol = prm.cg_rtol > 0.0 ? prm.cg_rtol : (dtype == MVTV_F64 ? 1e-12 : 1e-5);
+  const int cg_maxit = prm.cg_maxit > 0 ? prm.cg_maxit : (dtype == MVTV_F64 ? 20000 : 1000);
+  if (prm.precond != MVTV_PRECOND_JACOBI)
+    throw Error(MVTV_ERR_UNSUPPORTED, "only MVTV_PRECOND_JACOBI is implemented");
+  const long long launches0 = launches;
+  const long long nvec = dt.usz;
+  T *th = (T *)theta;
+
+  // ---- initial state: cpp :92-108 ; rcpp :98-109 ; py :54-65 -----------------------------------
+  if (!((prm.flags & MVTV_WARM_THETA_FROM_PLAN) && have_theta_state)) {
+    if (theta_init) {
+      double *stg = stage(sizeof(double) * (size_t)dt.Nloc);
+      MVTV_CUDA(cudaMemcpyAsync(stg, theta_init, sizeof(double) * (size_t)dt.Nloc, cudaMemcpyHostToDevice, stream));
+      k_import<T><<<grid1d(dt.Nloc), 256, 0, stream>>>(th, stg, dt.plane, dt.Nloc);
+    } else {
+      k_fill<T><<<grid1d(nvec), 256, 0, stream>>>(th, nvec, (T)mean_y);
+    }
+    launches += 1;
+  }
+  double rho, rhoM = (prm.rho_matrix0 == prm.rho_matrix0) ? prm.rho_matrix0 : lambda;
+  if (mode == MVTV_MODE_RCPP) {
+    if ((prm.flags & MVTV_WARM_U_FROM_PLAN) && have_u_state) {
+      // keep u[ucur], uscale
+    } else if (u_inout) {
+      double *stg = stage(sizeof(double) * (size_t)rt.R);
+      MVTV_CUDA(cudaMemcpyAsync(stg, u_inout, sizeof(double) * (size_t)rt.R, cudaMemcpyHostToDevice, stream));
+      k_u_convert<T><<<dim3(grid1d(dt.Nloc), bt.K), 256, 0, stream>>>(dt, rt, (T *)u[ucur], stg, 1.0, 1);
+      uscale = 1.0;
+      launches += 1;
+    } else {
+      MVTV_CUDA(cudaMemsetAsync(u[ucur], 0, (size_t)nvec * bt.K * esz(), stream));
+      uscale = 1.0;
+    }
+    rho = (prm.rho_init == prm.rho_init) ? prm.rho_init : lambda / 5.0;
+  } else {
+    k_fill<T><<<grid1d(nvec * bt.K), 256, 0, stream>>>((T *)u[ucur], nvec * bt.K, (T)(1.0 / lambda));
+    launches += 1;
+    uscale = 1.0;
+    rho = (mode == MVTV_MODE_CPP) ? (double)(int)lambda : lambda;  // int rho = lambda;  cpp :108
+  }
+  MVTV_CUDA(cudaGetLastError());
+  exchange_ghosts<T>(th);
+
+  // first loop test of the |dtheta| modes: thetaold = mean(y) - 0.1 (cpp :103-104) / - 1 (py :63)
+  double dmax = 0.0;
+  if (mode != MVTV_MODE_RCPP) {
+    const double c0 = mean_y - (mode == MVTV_MODE_CPP ? 0.1 : 1.0);
+    k_maxabs_const<T><<<std::min<int>(grid1d(dt.Nloc), (int)nblocks), 256, 0, stream>>>(
+        th, dt.plane, dt.Nloc, c0, RedBuf{partials, counters + 4}, zr);
+    launches += 1;
+    allreduce(zr, 1, ncclMax);
+    read_scalars<T>(zr, 1);
+    dmax = h_scal[0];
+  }
+
+  MVTV_CUDA(cudaEventRecord(ev0, stream));
+  // alpha = D*theta (cpp :100): only D^T alpha and D^T u are needed, computed by the init pass
+  launch_zu<T>(0.0, uscale, mode, 1, false);
+
+  int counter = 1, passes = 0, status = MVTV_OK;
+  double dual_norm = 1.0, primal_norm = 1.0, eps_dual = tol, eps_primal = tol;  // rcpp :108-109
+  double r_norm = NAN, s_norm = NAN;
+  long long inner = 0;
+  const double sqrtN = sqrt((double)N), sqrtR = sqrt((double)rt.R);
+  for (;;) {
+    if (mode == MVTV_MODE_RCPP) {
+      if (!(dual_norm > eps_dual || primal_norm > eps_primal)) break;  // rcpp :110
+    } else {
+      if (!(dmax > tol)) break;  // cpp :113 any(abs(theta-thetaold) > TOL)
+    }
+    if (prm.max_passes > 0 && passes >= prm.max_passes) break;
+    // b = Oty + rho*Dt*(alpha+u) ; theta = spsolve(sp_crosses, b)     cpp :115-116 / rcpp :112-113
+    int cgst = MVTV_OK;
+    switch (dt.P) {
+      case 2: cg_solve<T, 2>(rho, uscale, rhoM, cg_rtol, cg_maxit, inner, cgst); break;
+      case 3: cg_solve<T, 3>(rho, uscale, rhoM, cg_rtol, cg_maxit, inner, cgst); break;
+      case 4: cg_solve<T, 4>(rho, uscale, rhoM, cg_rtol, cg_maxit, inner, cgst); break;
+      default: throw Error(MVTV_ERR_UNSUPPORTED, "p must be 1..4");
+    }
+    if (cgst != MVTV_OK) { status = cgst; break; }
+    exchange_ghosts<T>(th);
+    // alpha, residuals, u update: cpp :117-120 / rcpp :114-117
+    const double kappa = (rho != 0.0) ? lambda / rho : INFINITY;
+    launch_zu<T>(kappa, uscale, mode, 0, true);
+    ucur ^= 1;
+    uscale = 1.0;
+    read_scalars<T>(zr, ZR_N);
+    r_norm = sqrt(h_scal[ZR_R2]);
+    s_norm = fabs(rho) * sqrt(h_scal[ZR_S2]);
+    dmax = h_scal[ZR_DMAX];
+    ++passes;
+    if (mode == MVTV_MODE_PY) continue;  // no residuals, no adaptation; counter never moves (py :65-76)
+    if (mode == MVTV_MODE_CPP) {
+      counter += 1;
+      if (counter > max_counter) { status = MVTV_ERR_NOT_CONVERGED; break; }  // cpp :122-124
+      double rho_next = rho;
+      if (r_norm > 20 * s_norm) { rho_next = 20 * rho; uscale = 0.05; }        // cpp :75-79
+      else if (s_norm > 20 * r_norm) { rho_next = 0.1 * rho; uscale = 10.0; }  // cpp :80-83
+      rho = (double)(int)rho_next;                                             // cpp :126 (int rho)
+    } else {
+      dual_norm = s_norm;                                                       // rcpp :119
+      primal_norm = r_norm;                                                     // rcpp :120
+      eps_dual = tol * (sqrtN + sqrt(h_scal[ZR_DTU2]));                         // rcpp :121
+      eps_primal = tol * (sqrtR + std::max(sqrt(h_scal[ZR_DTH2]), sqrt(h_scal[ZR_AL2])));  // rcpp :122
+      if (r_norm > 10 * s_norm) { rho = 2.0 * rho; uscale = 1.0 / 2.0; }        // rcpp :82-85
+      else if (s_norm > 10 * r_norm) { rho = 1.0 / 2.0 * rho; uscale = 2.0; }   // rcpp :86-89
+      rhoM = rho;                                                               // rcpp :126
+      counter += 1;
+      if (counter > max_counter) { status = MVTV_ERR_NOT_CONVERGED; break; }    // rcpp :129-132
+    }
+  }
+  MVTV_CUDA(cudaEventRecord(ev1, stream));
+  MVTV_CUDA(cudaStreamSynchronize(stream));
+  prof_flush();
+  float ms = 0.f;
+  MVTV_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  have_theta_state = true;
+  have_u_state = true;
+  rho_state = rho;
+
+  // ---- outputs: theta, fitted = O*theta (cpp :65-66), u, rho ------------------------------------
+  if (theta_out) {
+    double *stg = stage(sizeof(double) * (size_t)dt.Nloc);
+    k_export<T><<<grid1d(dt.Nloc), 256, 0, stream>>>(stg, th, dt.plane, dt.Nloc);
+    MVTV_CUDA(cudaMemcpyAsync(theta_out, stg, sizeof(double) * (size_t)dt.Nloc, cudaMemcpyDeviceToHost, stream));
+    MVTV_CUDA(cudaStreamSynchronize(stream));
+    launches += 1;
+  }
+  if (fitted_out) {
+    double *stg = stage(sizeof(double) * (size_t)n);
+    launch_gather<T>(n, vid, th, dt.plane, dt.z0, dt.nz, stg, stream);
+    MVTV_CUDA(cudaMemcpyAsync(fitted_out, stg, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, stream));
+    MVTV_CUDA(cudaStreamSynchronize(stream));
+    launches += 1;
+  }
+  if (u_inout) {
+    double *stg = stage(sizeof(double) * (size_t)rt.R);
+    k_u_convert<T><<<dim3(grid1d(dt.Nloc), bt.K), 256, 0, stream>>>(dt, rt, (T *)u[ucur], stg, uscale, 0);
+    MVTV_CUDA(cudaMemcpyAsync(u_inout, stg, sizeof(double) * (size_t)rt.R, cudaMemcpyDeviceToHost, stream));
+    MVTV_CUDA(cudaStreamSynchronize(stream));
+    launches += 1;
+  }
+  MVTV_CUDA(cudaGetLastError());
+  res.counter = counter;
+  res.passes = passes;
+  res.status = status;
+  res.rho = rho;
+  res.r_norm = r_norm;
+  res.s_norm = s_norm;
+  res.max_dtheta = dmax;
+  res.inner_iters = inner;
+  res.device_seconds = (double)ms * 1e-3;
+  res.kernel_launches = launches - launches0;
+  return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+template <typename F>
+static int guarded(F &&f) {
+  try {
+    return f();
+  } catch (const Error &e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception &e) {
+    set_last_error(e.what());
+    return MVTV_ERR_INVALID;
+  }
+}
+
+extern "C" {
+
+int mvtv_abi_version(void) { return MVTV_ABI_VERSION; }
+const char *mvtv_last_error(void) { return g_last_error.c_str(); }
+
+int mvtv_device_count(int *count) {
+  return guarded([&] {
+    MVTV_REQUIRE(count, "null count");
+    *count = 0;
+    MVTV_CUDA(cudaGetDeviceCount(count));
+    return MVTV_OK;
+  });
+}
+
+int mvtv_nccl_unique_id(void *out128) {
+  return guarded([&] {
+    MVTV_REQUIRE(out128, "null argument");
+    g_nccl.load();
+    ncclUniqueId id;
+    MVTV_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return MVTV_OK;
+  });
+}
+
+int mvtv_plan_create(mvtv_plan **out, const mvtv_plan_desc *d) {
+  return guarded([&] {
+    MVTV_REQUIRE(out && d, "null argument");
+    *out = nullptr;
+    MVTV_REQUIRE(d->struct_size == (int32_t)sizeof(mvtv_plan_desc), "mvtv_plan_desc size mismatch");
+    MVTV_REQUIRE(d->p >= 1 && d->p <= MVTV_MAXP, "p must be 1..4");
+    MVTV_REQUIRE(d->dtype == MVTV_F64 || d->dtype == MVTV_F32, "dtype must be 64 or 32");
+    MVTV_REQUIRE(d->variant == MVTV_VARIANT_REFERENCE || d->variant == MVTV_VARIANT_INTENDED, "bad variant");
+    MVTV_REQUIRE(d->world >= 1 && d->rank >= 0 && d->rank < d->world, "bad rank/world");
+    int ndev = 0;
+    MVTV_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) throw Error(MVTV_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    std::unique_ptr<mvtv_plan> pl(new mvtv_plan());
+    if (d->device >= 0) pl->device = d->device;
+    else MVTV_CUDA(cudaGetDevice(&pl->device));
+    MVTV_REQUIRE(pl->device < ndev, "device ordinal out of range");
+    pl->dtype = d->dtype;
+    pl->variant = d->variant;
+    pl->rank = d->rank;
+    pl->world = d->world;
+    pl->build_tables(*d);
+    pl->allocate();
+    if (d->world > 1) {
+      MVTV_REQUIRE(d->nccl_unique_id, "world > 1 needs nccl_unique_id");
+      g_nccl.load();
+      ncclUniqueId id;
+      memcpy(&id, d->nccl_unique_id, sizeof(id));
+      MVTV_NCCL(g_nccl.CommInitRank(&pl->comm, d->world, id, d->rank));
+    }
+    *out = pl.release();
+    return MVTV_OK;
+  });
+}
+
+int mvtv_plan_destroy(mvtv_plan *plan) {
+  return guarded([&] {
+    delete plan;
+    return MVTV_OK;
+  });
+}
+
+int mvtv_plan_info(const mvtv_plan *plan, int64_t *N, int64_t *R, int64_t *z0, int64_t *nz) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan, "null plan");
+    if (N) *N = plan->N;
+    if (R) *R = plan->rt.R;
+    if (z0) *z0 = plan->dt.z0;
+    if (nz) *nz = plan->dt.nz;
+    return MVTV_OK;
+  });
+}
+
+int mvtv_plan_profile(mvtv_plan *plan, int enable) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan, "null plan");
+    plan->prof_on = enable != 0;
+    for (int k = 0; k < MVTV_KC_N; ++k) { plan->prof_ms[k] = 0.0; plan->prof_cnt[k] = 0; }
+    return MVTV_OK;
+  });
+}
+
+int mvtv_plan_get_profile(mvtv_plan *plan, double *ms, int64_t *count) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && ms && count, "null argument");
+    for (int k = 0; k < MVTV_KC_N; ++k) { ms[k] = plan->prof_ms[k]; count[k] = plan->prof_cnt[k]; }
+    return MVTV_OK;
+  });
+}
+
+int mvtv_plan_set_points_dev(mvtv_plan *plan, int64_t n, const double *data_dev, const double *y_dev,
+                             const double *axes_dev) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && data_dev && y_dev && axes_dev, "null argument");
+    if (plan->dtype == MVTV_F64) plan->set_points_t<double>(n, data_dev, y_dev, axes_dev);
+    else plan->set_points_t<float>(n, data_dev, y_dev, axes_dev);
+    return MVTV_OK;
+  });
+}
+
+int mvtv_plan_set_points(mvtv_plan *plan, int64_t n, const double *data, const double *y, const double *axes) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && data && y && axes, "null argument");
+    MVTV_REQUIRE(n >= 1, "n must be >= 1");
+    plan->use_device();
+    long long na = 0;
+    for (int a = 0; a < plan->p; ++a) na += plan->dt.m[a];
+    const size_t nd = (size_t)n * plan->p, total = nd + (size_t)n + (size_t)na;
+    double *buf = nullptr;
+    MVTV_CUDA(cudaMalloc(&buf, sizeof(double) * total));
+    int rc = MVTV_OK;
+    try {
+      MVTV_CUDA(cudaMemcpyAsync(buf, data, sizeof(double) * nd, cudaMemcpyHostToDevice, plan->stream));
+      MVTV_CUDA(cudaMemcpyAsync(buf + nd, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, plan->stream));
+      MVTV_CUDA(cudaMemcpyAsync(buf + nd + n, axes, sizeof(double) * (size_t)na, cudaMemcpyHostToDevice, plan->stream));
+      if (plan->dtype == MVTV_F64) plan->set_points_t<double>(n, buf, buf + nd, buf + nd + n);
+      else plan->set_points_t<float>(n, buf, buf + nd, buf + nd + n);
+    } catch (...) {
+      cudaFree(buf);
+      throw;
+    }
+    MVTV_CUDA(cudaFree(buf));
+    return rc;
+  });
+}
+
+int mvtv_plan_get_cache(mvtv_plan *plan, double *Oty, double *counts, int64_t *vertex_of_point) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && plan->have_points, "no points set");
+    plan->use_device();
+    const long long nl = plan->dt.Nloc;
+    double *stg = plan->stage(sizeof(double) * (size_t)nl);
+    for (int k = 0; k < 2; ++k) {
+      double *dst = k == 0 ? Oty : counts;
+      if (!dst) continue;
+      void *src = k == 0 ? plan->oty : plan->cnt;
+      if (plan->dtype == MVTV_F64)
+        k_export<double><<<mvtv_plan::grid1d(nl), 256, 0, plan->stream>>>(stg, (const double *)src, plan->dt.plane, nl);
+      else
+        k_export<float><<<mvtv_plan::grid1d(nl), 256, 0, plan->stream>>>(stg, (const float *)src, plan->dt.plane, nl);
+      MVTV_CUDA(cudaMemcpyAsync(dst, stg, sizeof(double) * (size_t)nl, cudaMemcpyDeviceToHost, plan->stream));
+      MVTV_CUDA(cudaStreamSynchronize(plan->stream));
+    }
+    if (vertex_of_point) {
+      MVTV_CUDA(cudaMemcpyAsync(vertex_of_point, plan->vid, sizeof(long long) * (size_t)plan->n,
+                                cudaMemcpyDeviceToHost, plan->stream));
+      MVTV_CUDA(cudaStreamSynchronize(plan->stream));
+    }
+    return MVTV_OK;
+  });
+}
+
+int mvtv_solve(mvtv_plan *plan, const mvtv_solve_params *prm, const double *theta_init, double *u_inout,
+               double *theta_out, double *fitted_out, mvtv_solve_result *res) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && prm && res, "null argument");
+    MVTV_REQUIRE(prm->struct_size == (int32_t)sizeof(mvtv_solve_params), "mvtv_solve_params size mismatch");
+    memset(res, 0, sizeof(*res));
+    int st;
+    if (plan->dtype == MVTV_F64) st = plan->solve_t<double>(*prm, theta_init, u_inout, theta_out, fitted_out, *res);
+    else st = plan->solve_t<float>(*prm, theta_init, u_inout, theta_out, fitted_out, *res);
+    if (st == MVTV_ERR_NOT_CONVERGED) set_last_error("Failed to converge!");
+    if (st == MVTV_ERR_INNER_SOLVE) set_last_error("x-update CG did not reach cg_rtol within cg_maxit");
+    return st;
+  });
+}
+
+int mvtv_predict(mvtv_plan *plan, int64_t n_new, const double *data, const double *axes, const double *theta,
+                 double *fits_out) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && data && axes && fits_out, "null argument");
+    MVTV_REQUIRE(n_new >= 1, "n_new must be >= 1");
+    plan->use_device();
+    cudaStream_t s = plan->stream;
+    long long na = 0;
+    for (int a = 0; a < plan->p; ++a) na += plan->dt.m[a];
+    const long long nl = plan->dt.Nloc;
+    const size_t nd = (size_t)n_new * plan->p;
+    // staging: [data | axes | vid (as 8-byte) | out | theta(ghosted, double)]
+    const size_t total = nd + (size_t)na + (size_t)n_new * 2 + (size_t)plan->dt.usz;
+    double *buf = plan->stage(sizeof(double) * total);
+    double *d_data = buf, *d_axes = buf + nd;
+    long long *d_vid = (long long *)(d_axes + na);
+    double *d_out = (double *)(d_vid + n_new);
+    double *d_theta = d_out + n_new;
+    MVTV_CUDA(cudaMemcpyAsync(d_data, data, sizeof(double) * nd, cudaMemcpyHostToDevice, s));
+    MVTV_CUDA(cudaMemcpyAsync(d_axes, axes, sizeof(double) * (size_t)na, cudaMemcpyHostToDevice, s));
+    launch_bin(plan->p, plan->dt, n_new, d_data, d_axes, d_vid, nullptr, nullptr, s);
+    if (theta) {
+      MVTV_CUDA(cudaMemcpyAsync(d_theta + plan->dt.plane, theta, sizeof(double) * (size_t)nl, cudaMemcpyHostToDevice, s));
+      launch_gather<double>(n_new, d_vid, d_theta, plan->dt.plane, plan->dt.z0, plan->dt.nz, d_out, s);
+    } else {
+      MVTV_REQUIRE(plan->have_theta_state, "theta == NULL needs a previous mvtv_solve on this plan");
+      if (plan->dtype == MVTV_F64)
+        launch_gather<double>(n_new, d_vid, (const double *)plan->theta, plan->dt.plane, plan->dt.z0, plan->dt.nz, d_out, s);
+      else
+        launch_gather<float>(n_new, d_vid, (const float *)plan->theta, plan->dt.plane, plan->dt.z0, plan->dt.nz, d_out, s);
+    }
+    MVTV_CUDA(cudaMemcpyAsync(fits_out, d_out, sizeof(double) * (size_t)n_new, cudaMemcpyDeviceToHost, s));
+    MVTV_CUDA(cudaStreamSynchronize(s));
+    plan->launches += 2;
+    return MVTV_OK;
+  });
+}
+
+int mvtv_apply_D(mvtv_plan *plan, const double *theta, double *out_rows) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && theta && out_rows, "null argument");
+    MVTV_REQUIRE(plan->world == 1, "operator-level entry points are single-GPU");
+    plan->use_device();
+    cudaStream_t s = plan->stream;
+    const size_t nv = (size_t)plan->dt.usz, R = (size_t)plan->rt.R;
+    double *buf = plan->stage(sizeof(double) * (nv + R + 1));
+    MVTV_CUDA(cudaMemsetAsync(buf, 0, sizeof(double) * nv, s));
+    MVTV_CUDA(cudaMemcpyAsync(buf + plan->dt.plane, theta, sizeof(double) * (size_t)plan->dt.Nloc, cudaMemcpyHostToDevice, s));
+    k_apply_D<<<dim3(mvtv_plan::grid1d(plan->dt.Nloc), plan->bt.K), 256, 0, s>>>(plan->dt, plan->bt, plan->rt, buf, buf + nv);
+    MVTV_CUDA(cudaGetLastError());
+    MVTV_CUDA(cudaMemcpyAsync(out_rows, buf + nv, sizeof(double) * R, cudaMemcpyDeviceToHost, s));
+    MVTV_CUDA(cudaStreamSynchronize(s));
+    plan->launches += 1;
+    return MVTV_OK;
+  });
+}
+
+int mvtv_apply_Dt(mvtv_plan *plan, const double *rows, double *out_vertices) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && rows && out_vertices, "null argument");
+    MVTV_REQUIRE(plan->world == 1, "operator-level entry points are single-GPU");
+    plan->use_device();
+    cudaStream_t s = plan->stream;
+    const size_t nv = (size_t)plan->dt.usz, R = (size_t)plan->rt.R;
+    double *buf = plan->stage(sizeof(double) * (nv + R + 1));
+    MVTV_CUDA(cudaMemcpyAsync(buf + nv, rows, sizeof(double) * R, cudaMemcpyHostToDevice, s));
+    k_apply_Dt<<<plan->grid_owned(), 256, 0, s>>>(plan->dt, plan->bt, plan->rt, buf + nv, buf);
+    MVTV_CUDA(cudaGetLastError());
+    MVTV_CUDA(cudaMemcpyAsync(out_vertices, buf + plan->dt.plane, sizeof(double) * (size_t)plan->dt.Nloc,
+                              cudaMemcpyDeviceToHost, s));
+    MVTV_CUDA(cudaStreamSynchronize(s));
+    plan->launches += 1;
+    return MVTV_OK;
+  });
+}
+
+int mvtv_apply_M(mvtv_plan *plan, double sc, const double *x, double *out) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && x && out, "null argument");
+    MVTV_REQUIRE(plan->world == 1, "operator-level entry points are single-GPU");
+    MVTV_REQUIRE(plan->have_points, "mvtv_apply_M needs the point counts: call mvtv_plan_set_points first");
+    plan->use_device();
+    cudaStream_t s = plan->stream;
+    const size_t nv = (size_t)plan->dt.usz;
+    double *buf = plan->stage(sizeof(double) * nv * 3);
+    double *dx = buf, *dc = buf + nv, *dout = buf + 2 * nv;
+    MVTV_CUDA(cudaMemsetAsync(buf, 0, sizeof(double) * nv * 3, s));
+    MVTV_CUDA(cudaMemcpyAsync(dx + plan->dt.plane, x, sizeof(double) * (size_t)plan->dt.Nloc, cudaMemcpyHostToDevice, s));
+    if (plan->dtype == MVTV_F64)
+      MVTV_CUDA(cudaMemcpyAsync(dc, plan->cnt, sizeof(double) * nv, cudaMemcpyDeviceToDevice, s));
+    else {
+      // counts are small integers: widen exactly
+      k_export<float><<<mvtv_plan::grid1d(plan->dt.Nloc), 256, 0, s>>>(dc + plan->dt.plane, (const float *)plan->cnt,
+                                                                       plan->dt.plane, plan->dt.Nloc);
+    }
+    const dim3 g = plan->grid_owned();
+    switch (plan->dt.P) {
+      case 2: k_apply_M<double, 2><<<g, 256, 0, s>>>(plan->dt, plan->st, dx, dc, sc, dout); break;
+      case 3: k_apply_M<double, 3><<<g, 256, 0, s>>>(plan->dt, plan->st, dx, dc, sc, dout); break;
+      case 4: k_apply_M<double, 4><<<g, 256, 0, s>>>(plan->dt, plan->st, dx, dc, sc, dout); break;
+      default: throw Error(MVTV_ERR_UNSUPPORTED, "p must be 1..4");
+    }
+    MVTV_CUDA(cudaGetLastError());
+    MVTV_CUDA(cudaMemcpyAsync(out, dout + plan->dt.plane, sizeof(double) * (size_t)plan->dt.Nloc, cudaMemcpyDeviceToHost, s));
+    MVTV_CUDA(cudaStreamSynchronize(s));
+    plan->launches += 1;
+    return MVTV_OK;
+  });
+}
+
+int mvtv_softthresh(int64_t n, const double *z, double lam, double *out) {
+  return guarded([&] {
+    MVTV_REQUIRE(n >= 0 && (n == 0 || (z && out)), "bad argument");
+    if (n == 0) return (int)MVTV_OK;
+    double *buf = nullptr;
+    MVTV_CUDA(cudaMalloc(&buf, sizeof(double) * (size_t)n * 2));
+    cudaError_t e = cudaMemcpy(buf, z, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      k_softthresh<<<mvtv_plan::grid1d(n), 256>>>(buf, lam, buf + n, n);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, buf + n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    MVTV_CUDA(e);
+    return (int)MVTV_OK;
+  });
+}
+
+int mvtv_nearest(int p, const int64_t *m, const double *axes, int64_t n, const double *data, int64_t *vertex_out) {
+  return guarded([&] {
+    MVTV_REQUIRE(p >= 1 && p <= MVTV_MAXP && m && axes && data && vertex_out && n >= 1, "bad argument");
+    DimTab dt{};
+    dt.P = p;
+    long long na = 0, s = 1;
+    for (int a = 0; a < p; ++a) {
+      dt.m[a] = m[a];
+      dt.stride[a] = s;
+      s *= m[a];
+      na += m[a];
+    }
+    const size_t nd = (size_t)n * p;
+    double *buf = nullptr;
+    MVTV_CUDA(cudaMalloc(&buf, sizeof(double) * (nd + (size_t)na + (size_t)n)));
+    long long *d_vid = (long long *)(buf + nd + na);
+    cudaError_t e = cudaMemcpy(buf, data, sizeof(double) * nd, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(buf + nd, axes, sizeof(double) * (size_t)na, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      try {
+        launch_bin(p, dt, n, buf, buf + nd, d_vid, nullptr, nullptr, nullptr);
+      } catch (...) {
+        cudaFree(buf);
+        throw;
+      }
+      e = cudaMemcpy(vertex_out, d_vid, sizeof(long long) * (size_t)n, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(buf);
+    MVTV_CUDA(e);
+    return (int)MVTV_OK;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(multivartv_b200.Plan -> libmvtv_b200.so); the oracle is only the checker.
+
+Bars: integer/index work bit-exact; fp64 solves: identical Counter / passes and max|theta - theta_oracle| <= 1e-9;
+fp32 mode: <= 1e-4 (stated in each test)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import py_oracle as po
+from tests.helpers import synth
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-9
+FP32_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def mv():
+    import multivartv_b200 as m
+    from multivartv_b200 import build
+    build.build()
+    return m
+
+
+def _axes_from_mesh(mesh, m):
+    axes, stride = [], 1
+    for k in range(len(m)):
+        axes.append(np.ascontiguousarray(mesh[::stride, k][: m[k]]))
+        stride *= int(m[k])
+    return axes
+
+
+# ---------------------------------------------------------------------------------------------
+# operators
+# ---------------------------------------------------------------------------------------------
+OPS = [([9], None, 0), ([7, 5], None, 0), ([7, 5], [0.25, 0.5], 0), ([1, 6], None, 0), ([6, 1], None, 0),
+       ([6, 6, 6], None, 0), ([5, 5, 5], [0.3, 0.5, 2.0], 0), ([3, 3, 4], None, 0), ([4, 5, 6], None, 1),
+       ([4, 4, 4, 4], [0.5, 0.25, 2.0, 3.0], 0), ([3, 3, 3, 3], None, 0), ([3, 4, 2, 5], None, 1), ([2, 2], None, 0)]
+
+
+@pytest.mark.parametrize("dims,deltas,variant", OPS)
+def test_D_Dt_M_match_oracle(mv, dims, deltas, variant):
+    """D*theta, Dt*w in the reference row order and (crossO + s*crossD)*x vs the matrix-free C oracle
+    (itself pinned to the reference's materialised D by tests/test_oracle_operators.py)."""
+    op = co.Operator(dims, deltas, variant)
+    rng = np.random.RandomState(len(dims) * 100 + sum(dims))
+    th, w = rng.normal(size=op.N), rng.normal(size=op.R)
+    with mv.Plan(dims, deltas=deltas, variant=variant) as pl:
+        assert (pl.N, pl.R) == (op.N, op.R)
+        assert np.abs(pl.apply_D(th) - op.D(th)).max() <= 1e-13
+        assert np.abs(pl.apply_Dt(w) - op.Dt(w)).max() <= 1e-12
+        # system matrix: needs counts -> a few points
+        p = len(dims)
+        x = rng.uniform(0, 1, (50, p))
+        y = rng.normal(size=50)
+        axes = [np.linspace(0, 1, d) if d > 1 else np.array([0.5]) for d in dims]
+        pl.set_points(x, y, axes)
+        idx = co.nearest(dims, axes, x)
+        Oty, cnt = co.scatter(idx, y, op.N)
+        ref = cnt * th + 0.7 * op.Dt(op.D(th))
+        assert np.abs(pl.apply_M(0.7, th) - ref).max() <= 1e-11
+
+
+def test_noncubic_reference_operator_is_refused(mv):
+    """cpp-code/utils.cpp:187,216: the reference's sparse product does not conform -> error, not a guess."""
+    with pytest.raises(mv.MvtvError) as ei:
+        mv.Plan([3, 4, 5])
+    assert ei.value.code == 4
+
+
+def test_nearest_and_scatter_bit_exact(mv, golden):
+    x, m, mesh = golden["near2_x"], golden["near2_m"], golden["near2_mesh"]
+    axes = _axes_from_mesh(mesh, m)
+    assert np.array_equal(mv.nearest1(x, axes=axes), golden["near2_idx"])
+    assert np.array_equal(mv.nearest1(x, mesh=mesh, m=m), golden["near2_idx"])
+    # known answers of code/test_utils.py:40-57
+    assert list(mv.nearest1(np.array([0.1, 0.9]), axes=[np.array([0, 0.5, 1.0])])) == [0, 2]
+    # ties -> lowest index
+    ax = [np.array([0.0, 1.0, 2.0]), np.array([0.0, 1.0])]
+    pts = np.array([[0.5, 0.5], [1.5, 0.5], [1.0, 0.25]])
+    assert list(mv.nearest1(pts, axes=ax)) == [0, 1, 1]
+    # Oty / counts: bit-exact (same accumulation order as arma's Ot*y)
+    rng = np.random.RandomState(5)
+    n = 20000
+    xx = rng.uniform(-1, 1, (n, 2))
+    yy = rng.normal(size=n)
+    dims = [13, 11]
+    axes = po.mesh_axes(xx, dims, po.MODE_CPP)
+    with mv.Plan(dims) as pl:
+        pl.set_points(xx, yy, axes)
+        Oty, cnt, vid = pl.cache()
+    idx = co.nearest(dims, axes, xx)
+    Oty_ref, cnt_ref = co.scatter(idx, yy, 13 * 11)
+    assert np.array_equal(vid, idx)
+    assert np.array_equal(cnt, cnt_ref)
+    assert np.array_equal(Oty, Oty_ref)
+
+
+def test_softthresh_golden(mv, golden):
+    assert np.array_equal(mv.softthresh(golden["soft_z"], 0.9), golden["soft_out_0p9"])
+    assert np.all(mv.softthresh(golden["soft_z"], np.inf) == 0.0)
+    z = np.random.RandomState(0).normal(size=100001)
+    assert np.array_equal(mv.softthresh(z, 0.3), po.softthresh(z, 0.3))
+
+
+# ---------------------------------------------------------------------------------------------
+# solver: golden vectors produced by the reference's own Python prototype
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["solve2a", "solve2b", "solve2c", "solve3a", "solve1a"])
+def test_py_mode_golden(mv, golden, name):
+    x, y, m, mesh = golden[name + "_x"], golden[name + "_y"], golden[name + "_m"], golden[name + "_mesh"]
+    lam, rm = float(golden[name + "_lam"]), float(golden[name + "_rho_matrix"])
+    th0 = golden["solve2a_theta"] if name == "solve2b" else None
+    out = mv.mbs_one(x, y, m, theta_init=th0, mesh=mesh, tune=lam, mode="py", rho_matrix0=rm)
+    assert out["passes"] == int(golden[name + "_passes"])
+    assert out["counter"] == int(golden[name + "_counter"])
+    assert np.abs(out["theta.hat"] - golden[name + "_theta"]).max() <= FP64_TOL
+    assert np.abs(out["fitted"] - golden[name + "_fitted"]).max() <= FP64_TOL
+
+
+def test_lambda_max_property(mv):
+    """code/test_solvers.py:24-29."""
+    x, y = synth(117, 10000, 2)
+    out = mv.mbs_one(x, y, [10, 10], tune=1e4, mode="py")
+    a, b, c = np.round(np.mean(out["theta.hat"]), 3), np.round(np.mean(out["fitted"]), 3), np.round(np.mean(y), 3)
+    assert a == b == c
+
+
+# ---------------------------------------------------------------------------------------------
+# solver: CPP / RCPP / PY loops vs the oracle
+# ---------------------------------------------------------------------------------------------
+def _check(out, ref, tol=FP64_TOL):
+    assert out["counter"] == ref["counter"], (out["counter"], ref["counter"])
+    assert np.abs(out["theta"] - ref["theta"]).max() <= tol
+    assert np.abs(out["fitted"] - ref["fitted"]).max() <= tol
+
+
+@pytest.mark.parametrize("mode", ["cpp", "rcpp", "py"])
+@pytest.mark.parametrize("lam", [0.2, 1.0, 1.5, 7.3])
+def test_config1_parity(mv, mode, lam):
+    """BASELINE config 1: 2-D, n=1000, 32x32 mesh, lambdas of rcpp-code/test_mbs_cpp2r.R:50 (+7.3)."""
+    imode = {"cpp": 0, "rcpp": 1, "py": 2}[mode]
+    x, y = synth(117, 1000, 2)
+    m = [32, 32]
+    axes = po.mesh_axes(x, m, imode)
+    ref = co.mbs_one(x, y, m, axes, lam, mode=imode)
+    with mv.Plan(m) as pl:
+        pl.set_points(x, y, axes)
+        out = pl.solve(lam, mode=mode, want_u=True)
+    _check(out, ref)
+    assert out["passes"] == ref["passes"]
+    assert np.abs(out["u"] - ref["u"]).max() <= 1e-8
+    assert abs(out["rho"] - ref["rho"]) <= 1e-12 * max(1.0, abs(ref["rho"]))
+    if mode == "cpp" and lam < 1:
+        assert out["counter"] == 3
+
+
+@pytest.mark.parametrize("mode", ["cpp", "rcpp"])
+@pytest.mark.parametrize("dims,deltas", [([6, 6, 6], None), ([5, 5, 5], "auto"), ([4, 4, 4, 4], None),
+                                          ([9, 7], "auto"), ([16], None), ([8, 8, 8], None), ([5, 5, 5, 5], "auto")])
+def test_p1234_parity(mv, mode, dims, deltas):
+    imode = {"cpp": 0, "rcpp": 1}[mode]
+    p = len(dims)
+    x, y = synth(7 + p, 400, p, 0.0, 1.0, 0.5)
+    axes = po.mesh_axes(x, dims, imode)
+    d = po.create_deltas(x, dims, imode) if deltas == "auto" else None
+    with mv.Plan(dims, deltas=d) as pl:
+        pl.set_points(x, y, axes)
+        for lam in (0.5, 3.0):
+            ref = co.mbs_one(x, y, dims, axes, lam, mode=imode, deltas=d)
+            out = pl.solve(lam, mode=mode)
+            _check(out, ref)
+
+
+def test_rcpp_warm_start_path(mv):
+    """rcpp mbs_path (solvers.cpp:204-222): theta, u, rho carried along the lambda path, through host
+    buffers (u_inout) and through the device-resident plan state (MVTV_WARM_*_FROM_PLAN)."""
+    x, y = synth(5, 500, 2)
+    m = [12, 12]
+    axes = po.mesh_axes(x, m, po.MODE_RCPP)
+    lams = [4.0, 1.0, 0.25]
+    th = u = None
+    rho = lams[0] / 5.0
+    refs = []
+    for lam in lams:
+        r = co.mbs_one(x, y, m, axes, lam, mode=co.MODE_RCPP, theta_init=th, u_init=u, rho_init=rho, rho_matrix0=rho)
+        refs.append(r)
+        th, u, rho = r["theta"], r["u"], r["rho"]
+    with mv.Plan(m) as pl:
+        pl.set_points(x, y, axes)
+        th = u = None
+        rho = lams[0] / 5.0
+        for lam, r in zip(lams, refs):
+            out = pl.solve(lam, mode="rcpp", theta_init=th, u_init=u, rho_init=rho, rho_matrix0=rho, want_u=True)
+            _check(out, r)
+            assert np.abs(out["u"] - r["u"]).max() <= 1e-8
+            th, u, rho = out["theta"], out["u"], out["rho"]
+    with mv.Plan(m) as pl:
+        pl.set_points(x, y, axes)
+        rho = lams[0] / 5.0
+        for i, (lam, r) in enumerate(zip(lams, refs)):
+            flags = 0 if i == 0 else (mv.WARM_THETA_FROM_PLAN | mv.WARM_U_FROM_PLAN)
+            out = pl.solve(lam, mode="rcpp", rho_init=rho, rho_matrix0=rho, flags=flags)
+            _check(out, r)
+            rho = out["rho"]
+
+
+def test_cpp_nonconvergence_raises(mv):
+    """cpp-code/solvers.cpp:122-124: throw std::invalid_argument("Failed to converge!")."""
+    x, y = synth(117, 1000, 2)
+    axes = po.mesh_axes(x, [32, 32], po.MODE_CPP)
+    with mv.Plan([32, 32]) as pl:
+        pl.set_points(x, y, axes)
+        with pytest.raises(mv.NotConverged) as ei:
+            pl.solve(7.3, mode="cpp", max_counter=3)
+        assert "Failed to converge!" in str(ei.value)
+        out = pl.solve(7.3, mode="rcpp", max_counter=5)   # rcpp: message + break, outputs filled
+        assert out["status"] == 3 and out["counter"] == 6
+
+
+def test_fp32_mode_tolerance(mv):
+    """north_star: fp32 mode reported at <= 1e-4 max-abs vs the fp64 oracle (same pass budget)."""
+    for dims in ([32, 32], [8, 8, 8], [5, 5, 5, 5]):
+        p = len(dims)
+        x, y = synth(11 + p, 2000, p, 0.0, 1.0, 0.5)
+        axes = po.mesh_axes(x, dims, po.MODE_RCPP)
+        ref = co.mbs_one(x, y, dims, axes, 1.0, mode=co.MODE_RCPP, max_passes=40)
+        with mv.Plan(dims, dtype=mv.F32) as pl:
+            pl.set_points(x, y, axes)
+            out = pl.solve(1.0, mode="rcpp", max_passes=40)
+        assert out["passes"] == ref["passes"] == 40
+        assert np.abs(out["theta"] - ref["theta"]).max() <= FP32_TOL
+
+
+def test_predict_and_mse(mv):
+    """mbs_predict / mse (cpp-code/solvers.cpp:154-168)."""
+    x, y = synth(21, 3000, 2)
+    out = mv.mbs_one(x, y, [16, 16], tune=0.8, mode="rcpp")
+    xn, _ = synth(22, 500, 2)
+    fits = mv.mbs_predict(out, xn)
+    ref = po.mbs_predict(out["theta.hat"], out["axes"], [16, 16], xn)
+    assert np.array_equal(fits, ref)
+    assert np.array_equal(mv.mbs_predict(out, x), out["fitted"])
+    assert mv.mbs_mse(out, y) == pytest.approx(po.mse(out["fitted"], y), rel=1e-15)
+
+
+# ---------------------------------------------------------------------------------------------
+# larger meshes: oracle with its iterative x-update on a bounded pass budget + size-independent properties
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims,n", [([256, 256], 65536), ([48, 48, 48], 60000), ([12, 12, 12, 12], 30000)])
+def test_midsize_parity_bounded_passes(mv, dims, n):
+    p = len(dims)
+    x, y = synth(31 + p, n, p, 0.0, 1.0, 0.5)
+    axes = po.mesh_axes(x, dims, po.MODE_RCPP)
+    ref = co.mbs_one(x, y, dims, axes, 1.0, mode=co.MODE_RCPP, max_passes=12, solver=co.SOLVER_PCG, cg_rtol=1e-13)
+    with mv.Plan(dims) as pl:
+        pl.set_points(x, y, axes)
+        out = pl.solve(1.0, mode="rcpp", max_passes=12, cg_rtol=1e-13, want_u=True)
+    assert out["passes"] == ref["passes"] == 12
+    assert np.abs(out["theta"] - ref["theta"]).max() <= FP64_TOL
+    assert np.abs(out["u"] - ref["u"]).max() <= 1e-8
+    assert out["rho"] == ref["rho"]
+    assert abs(out["r_norm"] - ref["r_norm"]) <= 1e-9 * max(1.0, ref["r_norm"])
+    assert abs(out["s_norm"] - ref["s_norm"]) <= 1e-9 * max(1.0, ref["s_norm"])
+
+
+def test_large_mesh_properties(mv):
+    """Size-independent checks at a size the oracle does not run: (i) theta solves the x-update's
+    normal equations to cg_rtol (apply_M residual), (ii) adjointness <D x, w> == <x, D^T w>,
+    (iii) constant data at large lambda returns the constant."""
+    dims = [1024, 1024]
+    N = dims[0] * dims[1]
+    rng = np.random.RandomState(3)
+    n = N
+    x = rng.uniform(0, 1, (n, 2))
+    f = (x[:, 0] > 0.5) * 1.0 + (x[:, 1] > 0.3) * 2.0
+    y = f + 0.5 * rng.normal(size=n)
+    axes = [np.linspace(0, 1, d) for d in dims]
+    with mv.Plan(dims) as pl:
+        th, w = rng.normal(size=pl.N), rng.normal(size=pl.R)
+        lhs = float(np.dot(pl.apply_D(th), w))
+        rhs = float(np.dot(th, pl.apply_Dt(w)))
+        assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs))
+        pl.set_points(x, y, axes)
+        # PY mode, one pass: theta = M^-1 (Oty + rho D^T(alpha+u)), alpha = D theta0 = 0, u = 1/lambda
+        lam = 2.0
+        out = pl.solve(lam, mode="py", max_passes=1, cg_rtol=1e-12)
+        Oty, cnt, _ = pl.cache()
+        b = Oty + lam * pl.apply_Dt(np.full(pl.R, 1.0 / lam))
+        res = pl.apply_M(lam, out["theta"]) - b
+        assert np.linalg.norm(res) <= 5e-12 * np.linalg.norm(b)
+        assert out["inner_iters"] > 0
+        # constant response
+        pl.set_points(x, np.full(n, 3.25), axes)
+        out = pl.solve(50.0, mode="rcpp", max_passes=30)
+        assert np.abs(out["theta"] - 3.25).max() <= 1e-9
