@@ -88,7 +88,7 @@ typedef struct {
   double tol;           /* NaN or <=0 -> the reference's TOL macro (1e-3 cpp/py, 1e-4 rcpp) */
   int32_t max_counter;  /* 0 -> reference default (2000 / 3000 / 5000) */
   int32_t max_passes;   /* >0: stop after this many ADMM passes (fixed-budget benchmarking) */
-  double cg_rtol;       /* x-update stops at ||b - M theta|| <= cg_rtol*||b||; <=0 -> 1e-12 (f64) / 1e-5 (f32) */
+  double cg_rtol;       /* x-update stops at ||b - M theta|| <= cg_rtol*||b||; <=0 -> 1e-13 (f64) / 1e-5 (f32) */
   int32_t cg_maxit;     /* 0 -> 20000 (f64) / 1000 (f32; reaching it is not an error in f32) */
   int32_t precond;      /* MVTV_PRECOND_* */
   uint32_t flags;       /* MVTV_WARM_* */
@@ -139,9 +139,8 @@ int mvtv_plan_set_points_dev(mvtv_plan *plan, int64_t n, const double *data_colm
 #define MVTV_KC_ZU 0        /* fused z/u update + D^T products + norms */
 #define MVTV_KC_ZU_INIT 1   /* same kernel, initial D^T D theta / D^T u pass */
 #define MVTV_KC_CG_INIT 2   /* b, r = b - M theta, p */
-#define MVTV_KC_CG_SPMV 3   /* q = M p, p.q */
+#define MVTV_KC_CG_STEP 3   /* p = z + beta p fused with q = M p, p.q */
 #define MVTV_KC_CG_UPDATE 4 /* theta, r update, r.z, r.r */
-#define MVTV_KC_CG_DIR 5    /* p = z + beta p */
 #define MVTV_KC_N 8
 int mvtv_plan_profile(mvtv_plan *plan, int enable);
 int mvtv_plan_get_profile(mvtv_plan *plan, double *ms, int64_t *count);

@@ -16,7 +16,7 @@ VARIANT_REFERENCE, VARIANT_INTENDED = 0, 1
 F64, F32 = 64, 32
 PRECOND_JACOBI, PRECOND_MG = 0, 1
 WARM_THETA_FROM_PLAN, WARM_U_FROM_PLAN = 1, 2
-KC_NAMES = ["zu", "zu_init", "cg_init", "cg_spmv", "cg_update", "cg_dir"]
+KC_NAMES = ["zu", "zu_init", "cg_init", "cg_step", "cg_update"]
 KC_N = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -6,9 +6,9 @@
 //               ||r||^2 ||s||^2 ||D^T u||^2 ||D theta||^2 ||alpha||^2 max|dtheta|
 //               (cpp-code/solvers.cpp:115,117-120,113 ; rcpp solvers.cpp:112,114-117,119-122)
 //   k_cg_init   b = Oty + rho*D^T(alpha+u) (never stored), r = b - M theta, p = M_J^-1 r     (solvers.cpp:115-116)
-//   k_cg_spmv   q = (diag(c) + s*D^T D) p  as a 3^P-point clamped stencil, p.q                (solvers.cpp:116)
+//   k_cg_step   p = M_J^-1 r + beta p fused with q = (diag(c) + s*D^T D) p (3^P-point clamped stencil out of
+//               shared-memory plane tiles, marching along the last axis), p.q                 (solvers.cpp:116)
 //   k_cg_update theta += a p, r -= a q, r.z, r.r
-//   k_cg_dir    p = M_J^-1 r + beta p
 #pragma once
 #include "mvtv_internal.cuh"
 
@@ -200,18 +200,20 @@ __device__ __forceinline__ int neighbour_offsets(const DimTab &dt, long long q, 
 
 template <typename T>
 struct CgArgs {
-  T *x;          // theta (ghosted slab), updated in place
-  T *xold;       // copy of theta before the x-update (for max|dtheta|)
-  T *r, *p, *q;  // ghosted slabs
-  const T *c;    // diag(O^T O) = points per vertex
+  T *x;            // theta (ghosted slab), updated in place
+  T *xold;         // copy of theta before the x-update (for max|dtheta|)
+  T *r, *q;        // ghosted slabs
+  T *pbuf[2];      // search direction, ping-pong by the parity of the iterations performed
+  const T *c;      // diag(O^T O) = points per vertex
+  const T *dinv;   // 1 / (c + rhoM * diag(D^T D)): Jacobi preconditioner
   const T *oty, *v1, *v2;
-  double *S;     // CS_* scalars
-  double *raw;   // multi-GPU: reductions land here, are all-reduced, then committed by k_cg_commit_*;
-                 // nullptr on one GPU (the reducing kernel's last thread commits directly)
-  double rho;    // multiplies D^T(alpha+u) in b
-  double uscale; // lazy rescale of u: b = Oty + rho*(v1 + uscale*v2)
-  double rhoM;   // scalar of the system matrix diag(c) + rhoM * D^T D
-  double rtol2;  // cg_rtol^2
+  double *S;       // CS_* scalars
+  double *raw;     // multi-GPU: reductions land here, are all-reduced, then committed by k_cg_commit_*;
+                   // nullptr on one GPU (the reducing kernel's last thread commits directly)
+  double rho;      // multiplies D^T(alpha+u) in b
+  double uscale;   // lazy rescale of u: b = Oty + rho*(v1 + uscale*v2)
+  double rhoM;     // scalar of the system matrix diag(c) + rhoM * D^T D
+  double rtol2;    // cg_rtol^2
 };
 
 __device__ __forceinline__ bool cg_done(const double *S, double rtol2) {
@@ -234,6 +236,22 @@ __device__ __forceinline__ void cg_commit_update(double *S, const double *r2) {
   S[CS_ITERS] += 1.0;
 }
 
+// dinv = 1 / (c + rhoM*diag(K)) on every plane that holds real data (ghost planes included)
+template <typename T, int P>
+__global__ void __launch_bounds__(256)
+k_make_dinv(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const T *c, double rhoM,
+            T *dinv) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int zl = (int)blockIdx.y - 1;  // -1 .. nz
+  if (q >= dt.plane) return;
+  if ((zl < 0 && !dt.has_lo) || (zl >= dt.nz && !dt.has_hi)) return;
+  long long om[P], op[P];
+  const int cls = neighbour_offsets<P>(dt, q, zl, om, op);
+  const long long base = (long long)(zl + 1) * dt.plane + q;
+  dinv[base] = T(1) / (c[base] + (T)rhoM * (T)st.diagK[cls]);
+}
+
+// r = b - M theta with b = Oty + rho*(D^T alpha + uscale*D^T u) (b is never stored); r.z, r.r, b.b
 template <typename T, int P>
 __global__ void __launch_bounds__(256)
 k_cg_init(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
@@ -243,18 +261,15 @@ k_cg_init(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   double red[3] = {0, 0, 0};
   if (q < dt.plane) {
     long long om[P], op[P];
-    const int cls = neighbour_offsets<P>(dt, q, zl, om, op);
+    neighbour_offsets<P>(dt, q, zl, om, op);
     const long long base = (long long)(zl + 1) * dt.plane + q;
     T kx = 0;
     StencilRec<T, P - 1>::run(a.x, base, 0, om, op, st, kx);
     const T xv = a.x[base];
-    const T cv = a.c[base];
     const T bv = a.oty[base] + (T)a.rho * (a.v1[base] + (T)a.uscale * a.v2[base]);
-    const T rv = bv - (cv * xv + (T)a.rhoM * kx);
-    const T dg = cv + (T)a.rhoM * (T)st.diagK[cls];
-    const T zv = rv / dg;
+    const T rv = bv - (a.c[base] * xv + (T)a.rhoM * kx);
+    const T zv = rv * a.dinv[base];
     a.r[base] = rv;
-    a.p[base] = zv;
     a.xold[base] = xv;
     red[0] = (double)rv * (double)zv;
     red[1] = (double)rv * (double)rv;
@@ -265,29 +280,6 @@ k_cg_init(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
     if (raw) { raw[0] = res[0]; raw[1] = res[1]; raw[2] = res[2]; }
     else cg_commit_init(S, res);
   });
-}
-
-template <typename T, int P>
-__global__ void __launch_bounds__(256)
-k_cg_spmv(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
-          const RedBuf rb) {
-  if (cg_done(a.S, a.rtol2)) return;
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int zl = blockIdx.y;
-  double red[1] = {0};
-  if (q < dt.plane) {
-    long long om[P], op[P];
-    neighbour_offsets<P>(dt, q, zl, om, op);
-    const long long base = (long long)(zl + 1) * dt.plane + q;
-    T kp = 0;
-    StencilRec<T, P - 1>::run(a.p, base, 0, om, op, st, kp);
-    const T pv = a.p[base];
-    const T qv = a.c[base] * pv + (T)a.rhoM * kp;
-    a.q[base] = qv;
-    red[0] = (double)pv * (double)qv;
-  }
-  double *dst = a.raw ? a.raw : (a.S + CS_PQ);
-  grid_reduce<1, 1>(red, rb, [dst](const double (&res)[1]) { dst[0] = res[0]; });
 }
 
 // plain M*x for the ABI-level mvtv_apply_M
@@ -307,50 +299,208 @@ k_apply_M(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   }
 }
 
-template <typename T, int P>
-__global__ void __launch_bounds__(256)
-k_cg_update(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
-            const RedBuf rb) {
+// ---------------------------------------------------------------------------------------------
+// k_cg_step: fused CG direction update + SpMV.
+//   p_new = dinv.*r + beta*p_old        (never re-read from HBM: built tile by tile in shared memory)
+//   q     = (diag(c) + rhoM*K) p_new    (3^P-point clamped stencil out of shared memory)
+//   p.q
+// A CTA owns an in-plane tile (TX x TY x TW over axes 0..Q-1, Q = P-1) and marches along the last axis
+// over a chunk of planes, keeping four rolling planes of p_new (tile + 1-deep halo) in shared memory:
+// one __syncthreads per plane.  Algorithmic traffic: read r, dinv, p_old, c ; write p_new, q  (6 N).
+// ---------------------------------------------------------------------------------------------
+template <int Q, int TX_, int TY_, int TW_, int NT_>
+struct StepCfg {
+  static constexpr int TX = TX_, TY = TY_, TW = TW_, NT = NT_;
+  static constexpr int EX = TX + 2, EY = (Q >= 2 ? TY + 2 : 1), EW = (Q >= 3 ? TW + 2 : 1);
+  static constexpr int TE = EX * EY * EW;   // plane tile with halo
+  static constexpr int TI = TX * TY * TW;   // outputs per plane
+  static constexpr int NE = (TE + NT - 1) / NT;
+  static constexpr int NO = (TI + NT - 1) / NT;
+  static constexpr int SLOTS = 4;
+};
+
+template <typename T, int Q, typename Cfg>
+__device__ __forceinline__ T stencil_smem(const T *sm, const T *s0, const T *sp, int e0, const StencilTab &st) {
+  constexpr int EX = Cfg::EX, EY = Cfg::EY;
+  T acc = 0;
+#pragma unroll
+  for (int dz = 0; dz < 3; ++dz) {
+    const T *s = (dz == 0) ? sm : ((dz == 1) ? s0 : sp);
+    if constexpr (Q == 1) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) acc += (T)st.coef[dz * 3 + dx] * s[e0 + dx - 1];
+    } else if constexpr (Q == 2) {
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+          acc += (T)st.coef[(dz * 3 + dy) * 3 + dx] * s[e0 + (dy - 1) * EX + dx - 1];
+    } else {
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw)
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+            acc += (T)st.coef[((dz * 3 + dw) * 3 + dy) * 3 + dx] * s[e0 + (dw - 1) * EX * EY + (dy - 1) * EX + dx - 1];
+    }
+  }
+  return acc;
+}
+
+template <typename T, int Q, typename Cfg>
+__global__ void __launch_bounds__(Cfg::NT)
+k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
+          const RedBuf rb, const int zchunk) {
   if (cg_done(a.S, a.rtol2)) return;
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int zl = blockIdx.y;
-  double red[2] = {0, 0};
+  constexpr int TX = Cfg::TX, TY = Cfg::TY, TW = Cfg::TW, NT = Cfg::NT;
+  constexpr int EX = Cfg::EX, EY = Cfg::EY, TE = Cfg::TE, TI = Cfg::TI, NE = Cfg::NE, NO = Cfg::NO;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sp = reinterpret_cast<T *>(smem_raw);  // [SLOTS][TE]
+
+  const int tid = threadIdx.x;
+  const int it = (int)a.S[CS_ITERS];
+  const int cur = it & 1;
+  const bool first = (it == 0);
+  const T beta = first ? T(0) : (T)(a.S[2 * cur] / a.S[2 * (cur ^ 1)]);
+  const T *__restrict__ p_in = a.pbuf[cur];
+  T *__restrict__ p_out = a.pbuf[cur ^ 1];
+  const T *__restrict__ rr = a.r;
+  const T *__restrict__ dinv = a.dinv;
+
+  // in-plane tile origin
+  const int m0 = (int)dt.m[0];
+  const int m1 = (Q >= 2) ? (int)dt.m[1] : 1;
+  const int m2 = (Q >= 3) ? (int)dt.m[2] : 1;
+  const int ntx = (m0 + TX - 1) / TX;
+  const int nty = (m1 + TY - 1) / TY;
+  int bid = blockIdx.x;
+  const int bx = bid % ntx;
+  bid /= ntx;
+  const int by = bid % nty;
+  const int bw = bid / nty;
+  const int x0 = bx * TX, y0 = by * TY, w0 = bw * TW;
+
+  // loader bookkeeping: clamped in-plane source offset of each tile element this thread fills, and whether the
+  // element is an interior one inside the mesh (those are the vertices whose p_new this CTA writes back)
+  int src[NE];
+  bool wr[NE];
+#pragma unroll
+  for (int k = 0; k < NE; ++k) {
+    const int e = tid + k * NT;
+    int ex = e % EX, ey = (e / EX) % EY, ew = e / (EX * EY);
+    int gx = x0 + ex - 1, gy = (Q >= 2) ? y0 + ey - 1 : 0, gw = (Q >= 3) ? w0 + ew - 1 : 0;
+    bool interior = (ex >= 1 && ex <= TX && gx < m0);
+    if (Q >= 2) interior = interior && (ey >= 1 && ey <= TY && gy < m1);
+    if (Q >= 3) interior = interior && (ew >= 1 && ew <= TW && gw < m2);
+    gx = min(max(gx, 0), m0 - 1);
+    gy = min(max(gy, 0), m1 - 1);
+    gw = min(max(gw, 0), m2 - 1);
+    src[k] = gx + m0 * (gy + m1 * gw);
+    wr[k] = interior && (e < TE);
+  }
+
+  const int zc0 = blockIdx.y * zchunk;
+  const int zc1 = min(zc0 + zchunk, dt.nz);
+  const int zlo = dt.has_lo ? -1 : 0;          // lowest / highest local plane that holds real data
+  const int zhi = dt.has_hi ? dt.nz : dt.nz - 1;
+
+  // fill slot (z & 3) with plane clamp(z); write p_new back for planes this CTA owns (plus the ghost planes,
+  // which the first / last chunk keep up to date redundantly so p never needs a halo exchange)
+  auto load_plane = [&](int z) {
+    const int zs = min(max(z, zlo), zhi);
+    const bool own = (z == zs) && ((z >= zc0 && z < zc1) || (z < 0 && zc0 == 0) || (z >= dt.nz && zc1 == dt.nz));
+    T *dst = sp + ((z + 4) & 3) * TE;
+    const long long pb = (long long)(zs + 1) * dt.plane;
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+      const int e = tid + k * NT;
+      if (e < TE) {
+        const long long idx = pb + src[k];
+        T pn = dinv[idx] * rr[idx];
+        if (!first) pn += beta * p_in[idx];
+        dst[e] = pn;
+        if (own && wr[k]) p_out[idx] = pn;
+      }
+    }
+  };
+
+  double red[1] = {0.0};
+  load_plane(zc0 - 1);
+  load_plane(zc0);
+  for (int z = zc0; z < zc1; ++z) {
+    load_plane(z + 1);
+    __syncthreads();
+    const T *sm = sp + ((z + 3) & 3) * TE;
+    const T *s0 = sp + ((z + 4) & 3) * TE;
+    const T *s1 = sp + ((z + 5) & 3) * TE;
+    const long long pb = (long long)(z + 1) * dt.plane;
+#pragma unroll
+    for (int k = 0; k < NO; ++k) {
+      const int o = tid + k * NT;
+      if (o < TI) {
+        const int tx = o % TX, ty = (o / TX) % TY, tw = o / (TX * TY);
+        const int gx = x0 + tx, gy = y0 + ty, gw = w0 + tw;
+        if (gx < m0 && gy < m1 && gw < m2) {
+          const int e0 = (tx + 1) + EX * (((Q >= 2) ? ty + 1 : 0) + EY * ((Q >= 3) ? tw + 1 : 0));
+          const T kp = stencil_smem<T, Q, Cfg>(sm, s0, s1, e0, st);
+          const long long idx = pb + gx + (long long)m0 * (gy + (long long)m1 * gw);
+          const T pv = s0[e0];
+          const T qv = a.c[idx] * pv + (T)a.rhoM * kp;
+          a.q[idx] = qv;
+          red[0] += (double)pv * (double)qv;
+        }
+      }
+    }
+  }
+  double *dstp = a.raw ? a.raw : (a.S + CS_PQ);
+  grid_reduce<1, 1>(red, rb, [dstp](const double (&res)[1]) { dstp[0] = res[0]; });
+}
+
+// theta += alpha p ; r -= alpha q ; r.z ; r.r     (flat streaming kernel over the owned slab)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_cg_update(const CgArgs<T> a, const long long plane, const long long nloc, const RedBuf rb) {
+  if (cg_done(a.S, a.rtol2)) return;
   const int cur = ((int)a.S[CS_ITERS]) & 1;
   const T alpha = (T)(a.S[2 * cur] / a.S[CS_PQ]);
-  if (q < dt.plane) {
-    long long om[P], op[P];
-    const int cls = neighbour_offsets<P>(dt, q, zl, om, op);
-    const long long base = (long long)(zl + 1) * dt.plane + q;
-    const T pv = a.p[base];
-    const T rv = a.r[base] - alpha * a.q[base];
-    a.x[base] += alpha * pv;
-    a.r[base] = rv;
-    const T dg = a.c[base] + (T)a.rhoM * (T)st.diagK[cls];
-    red[0] = (double)rv * (double)(rv / dg);
-    red[1] = (double)rv * (double)rv;
+  const T *__restrict__ p = a.pbuf[cur ^ 1] + plane;
+  const T *__restrict__ q = a.q + plane;
+  const T *__restrict__ dinv = a.dinv + plane;
+  T *__restrict__ x = a.x + plane;
+  T *__restrict__ r = a.r + plane;
+  double red[2] = {0, 0};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < nloc; i += 4 * stride) {
+    T pv[4], qv[4], rv[4], xv[4], dv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long j = i + k * stride;
+      pv[k] = p[j]; qv[k] = q[j]; rv[k] = r[j]; xv[k] = x[j]; dv[k] = dinv[j];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long j = i + k * stride;
+      const T rn = rv[k] - alpha * qv[k];
+      x[j] = xv[k] + alpha * pv[k];
+      r[j] = rn;
+      red[0] += (double)rn * (double)(rn * dv[k]);
+      red[1] += (double)rn * (double)rn;
+    }
+  }
+  for (; i < nloc; i += stride) {
+    const T rn = r[i] - alpha * q[i];
+    x[i] += alpha * p[i];
+    r[i] = rn;
+    red[0] += (double)rn * (double)(rn * dinv[i]);
+    red[1] += (double)rn * (double)rn;
   }
   double *S = a.S, *raw = a.raw;
   grid_reduce<2, 2>(red, rb, [S, raw](const double (&res)[2]) {
     if (raw) { raw[0] = res[0]; raw[1] = res[1]; }
     else cg_commit_update(S, res);
   });
-}
-
-template <typename T, int P>
-__global__ void __launch_bounds__(256)
-k_cg_dir(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a) {
-  if (cg_done(a.S, a.rtol2)) return;  // also true right after the update that converged
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int zl = blockIdx.y;
-  const int n = ((int)a.S[CS_ITERS]) & 1;
-  const T beta = (T)(a.S[2 * n] / a.S[2 * (n ^ 1)]);
-  if (q < dt.plane) {
-    long long om[P], op[P];
-    const int cls = neighbour_offsets<P>(dt, q, zl, om, op);
-    const long long base = (long long)(zl + 1) * dt.plane + q;
-    const T dg = a.c[base] + (T)a.rhoM * (T)st.diagK[cls];
-    a.p[base] = a.r[base] / dg + beta * a.p[base];
-  }
 }
 
 // multi-GPU commits (after the all-reduce of `raw`)

@@ -103,7 +103,9 @@ struct mvtv_plan {
 
   // device state (element type = dtype)
   void *theta = nullptr, *xold = nullptr, *v1 = nullptr, *v2 = nullptr, *oty = nullptr, *cnt = nullptr;
-  void *r = nullptr, *pvec = nullptr, *q = nullptr;
+  void *r = nullptr, *q = nullptr, *dinv = nullptr;
+  void *pbuf[2] = {nullptr, nullptr};
+  double dinv_rho = NAN;  // rhoM the inverse diagonal was built for
   void *u[2] = {nullptr, nullptr};
   int ucur = 0;
   double uscale = 1.0;
@@ -182,7 +184,7 @@ struct mvtv_plan {
   ~mvtv_plan() {
     cudaSetDevice(device);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pvec, q, u[0], u[1], S, zr, raw, partials, counters, vid, staging};
+    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pbuf[0], pbuf[1], q, dinv, u[0], u[1], S, zr, raw, partials, counters, vid, staging};
     for (void *b : bufs)
       if (b) cudaFree(b);
     if (h_scal) cudaFreeHost(h_scal);
@@ -310,7 +312,7 @@ struct mvtv_plan {
     MVTV_CUDA(cudaEventCreate(&ev0));
     MVTV_CUDA(cudaEventCreate(&ev1));
     const size_t vb = (size_t)dt.usz * esz();
-    void **vecs[] = {&theta, &xold, &v1, &v2, &oty, &cnt, &r, &pvec, &q};
+    void **vecs[] = {&theta, &xold, &v1, &v2, &oty, &cnt, &r, &pbuf[0], &pbuf[1], &q, &dinv};
     for (void **v : vecs) {
       MVTV_CUDA(cudaMalloc(v, vb));
       MVTV_CUDA(cudaMemsetAsync(*v, 0, vb, stream));
@@ -323,7 +325,7 @@ struct mvtv_plan {
     grid = dim3((unsigned)((dt.plane + 255) / 256), (unsigned)(dt.nz + dt.has_lo), 1);
     MVTV_REQUIRE(grid.y <= 65535, "last mesh axis too long for grid.y");
     nblocks = grid.x * grid.y;
-    MVTV_CUDA(cudaMalloc(&partials, sizeof(double) * (size_t)nblocks * ZR_N));
+    MVTV_CUDA(cudaMalloc(&partials, sizeof(double) * (size_t)std::max<unsigned>(nblocks, 1u << 16) * ZR_N));
     MVTV_CUDA(cudaMalloc(&counters, sizeof(unsigned) * 8));
     MVTV_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned) * 8, stream));
     MVTV_CUDA(cudaMalloc(&S, sizeof(double) * CS_N));
@@ -404,6 +406,9 @@ struct mvtv_plan {
     }
     MVTV_CUDA(cudaFree(key_in));
     MVTV_CUDA(cudaFree(temp));
+    exchange_ghosts<T>((T *)cnt);   // diag(c) on the ghost planes feeds the redundant ghost-plane work
+    MVTV_CUDA(cudaStreamSynchronize(stream));
+    dinv_rho = NAN;
     n = npts;
     have_points = true;
     have_u_state = have_theta_state = false;
@@ -486,15 +491,31 @@ void mvtv_plan::launch_zu(double kappa, double usc, int mode, int init, bool wit
   }
 }
 
+// tile shapes of k_cg_step per mesh rank (in-plane tile x planes marched by one CTA)
+template <int P> struct StepShape;
+template <> struct StepShape<2> { using Cfg = StepCfg<1, 512, 1, 1, 256>; };
+template <> struct StepShape<3> { using Cfg = StepCfg<2, 64, 16, 1, 256>; };
+template <> struct StepShape<4> { using Cfg = StepCfg<3, 32, 8, 4, 256>; };
+
 template <typename T, int P>
 int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, long long &inner, int &status) {
+  using Cfg = typename StepShape<P>::Cfg;
+  constexpr int Q = P - 1;
+  if (!(dinv_rho == rhoM)) {
+    k_make_dinv<T, P><<<dim3(grid.x, (unsigned)dt.nz + 2, 1), block, 0, stream>>>(dt, st, (const T *)cnt, rhoM, (T *)dinv);
+    MVTV_CUDA(cudaGetLastError());
+    dinv_rho = rhoM;
+    launches += 1;
+  }
   CgArgs<T> a;
   a.x = (T *)theta;
   a.xold = (T *)xold;
   a.r = (T *)r;
-  a.p = (T *)pvec;
   a.q = (T *)q;
+  a.pbuf[0] = (T *)pbuf[0];
+  a.pbuf[1] = (T *)pbuf[1];
   a.c = (const T *)cnt;
+  a.dinv = (const T *)dinv;
   a.oty = (const T *)oty;
   a.v1 = (const T *)v1;
   a.v2 = (const T *)v2;
@@ -505,8 +526,6 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   a.rhoM = rhoM;
   a.rtol2 = rtol * rtol;
   const dim3 g = grid_owned();
-  const unsigned nb = g.x * g.y;
-  (void)nb;
   prof_begin(MVTV_KC_CG_INIT);
   k_cg_init<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1});
   prof_end();
@@ -517,30 +536,43 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     k_cg_commit_init<<<1, 1, 0, stream>>>(S, raw);
     launches += 1;
   }
+  // fused direction + SpMV launch shape: in-plane tiles x chunks of the last axis, ~4 CTAs per SM
+  const int m0 = (int)dt.m[0], m1 = Q >= 2 ? (int)dt.m[1] : 1, m2 = Q >= 3 ? (int)dt.m[2] : 1;
+  const unsigned tiles = (unsigned)(((m0 + Cfg::TX - 1) / Cfg::TX) * ((m1 + Cfg::TY - 1) / Cfg::TY) *
+                                    ((m2 + Cfg::TW - 1) / Cfg::TW));
+  int nchunk = (int)std::max<long long>(1, std::min<long long>(dt.nz, (148ll * 6 + tiles - 1) / tiles));
+  int zchunk = (dt.nz + nchunk - 1) / nchunk;
+  if (zchunk < 16) zchunk = std::min(16, dt.nz);   // keep the 2-plane prologue cheap
+  nchunk = (dt.nz + zchunk - 1) / zchunk;
+  const dim3 gs(tiles, (unsigned)nchunk, 1);
+  const size_t smem = sizeof(T) * (size_t)Cfg::SLOTS * Cfg::TE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Q, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int gu = (int)std::max<long long>(1, std::min<long long>(148 * 8, (dt.Nloc + 1023) / 1024));
   int launched = 0;
   int batch = std::max(2, std::min(last_cg_iters, 256));
   double iters = 0;
   for (;;) {
     for (int k = 0; k < batch; ++k) {
-      if (world > 1) exchange_ghosts<T>((T *)pvec);
-      prof_begin(MVTV_KC_CG_SPMV);
-      k_cg_spmv<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2});
+      if (world > 1) exchange_ghosts<T>((T *)r);
+      prof_begin(MVTV_KC_CG_STEP);
+      k_cg_step<T, Q, Cfg><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       prof_end();
       if (world > 1) {
         allreduce(raw, 1, ncclSum);
         k_cg_commit_pq<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
       }
       prof_begin(MVTV_KC_CG_UPDATE);
-      k_cg_update<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 3});
+      k_cg_update<T><<<gu, 256, 0, stream>>>(a, dt.plane, dt.Nloc, RedBuf{partials, counters + 3});
       prof_end();
       if (world > 1) {
         allreduce(raw, 2, ncclSum);
         k_cg_commit_update<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
       }
-      prof_begin(MVTV_KC_CG_DIR);
-      k_cg_dir<T, P><<<g, block, 0, stream>>>(dt, st, a);
-      prof_end();
-      launches += world > 1 ? 5 : 3;
+      launches += world > 1 ? 4 : 2;
     }
     MVTV_CUDA(cudaGetLastError());
     launched += batch;
@@ -578,7 +610,7 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
   const double tol = (prm.tol > 0.0) ? prm.tol : (mode == MVTV_MODE_RCPP ? 1e-4 : 1e-3);
   const int max_counter = prm.max_counter > 0 ? prm.max_counter
                           : (mode == MVTV_MODE_CPP ? 2000 : (mode == MVTV_MODE_RCPP ? 3000 : 5000));
-  const double cg_rtol = prm.cg_rtol > 0.0 ? prm.cg_rtol : (dtype == MVTV_F64 ? 1e-12 : 1e-5);
+  const double cg_rtol = prm.cg_rtol > 0.0 ? prm.cg_rtol : (dtype == MVTV_F64 ? 1e-13 : 1e-5);
   const int cg_maxit = prm.cg_maxit > 0 ? prm.cg_maxit : (dtype == MVTV_F64 ? 20000 : 1000);
   if (prm.precond != MVTV_PRECOND_JACOBI)
     throw Error(MVTV_ERR_UNSUPPORTED, "only MVTV_PRECOND_JACOBI is implemented");

@@ -166,11 +166,15 @@ def test_p1234_parity(mv, mode, dims, deltas):
     x, y = synth(7 + p, 400, p, 0.0, 1.0, 0.5)
     axes = po.mesh_axes(x, dims, imode)
     d = po.create_deltas(x, dims, imode) if deltas == "auto" else None
+    # delta-scaled blocks (the mbs() driver's operators) make diag(c) + rho*D^T D badly conditioned at
+    # empty vertices: the x-update needs a tighter residual than the default to stay within 1e-9 of the
+    # reference's direct solve
+    rtol = 1e-14 if deltas == "auto" else 0.0
     with mv.Plan(dims, deltas=d) as pl:
         pl.set_points(x, y, axes)
         for lam in (0.5, 3.0):
             ref = co.mbs_one(x, y, dims, axes, lam, mode=imode, deltas=d)
-            out = pl.solve(lam, mode=mode)
+            out = pl.solve(lam, mode=mode, cg_rtol=rtol)
             _check(out, ref)
 
 
@@ -224,7 +228,9 @@ def test_fp32_mode_tolerance(mv):
     """north_star: fp32 mode reported at <= 1e-4 max-abs vs the fp64 oracle (same pass budget)."""
     for dims in ([32, 32], [8, 8, 8], [5, 5, 5, 5]):
         p = len(dims)
-        x, y = synth(11 + p, 2000, p, 0.0, 1.0, 0.5)
+        rng = np.random.RandomState(11 + p)      # the BASELINE synthetic family: O(1) step function + N(0, 0.5)
+        x = rng.uniform(0, 1, (2000, p))
+        y = np.prod(x > 0.5, axis=1) * 1.0 + 0.5 * np.prod(x < 0.2, axis=1) + 0.5 * rng.normal(size=2000)
         axes = po.mesh_axes(x, dims, po.MODE_RCPP)
         ref = co.mbs_one(x, y, dims, axes, 1.0, mode=co.MODE_RCPP, max_passes=40)
         with mv.Plan(dims, dtype=mv.F32) as pl:
