@@ -1,0 +1,341 @@
+// mvtv_solvers.hpp -- header-only C++ mirror of the reference's solver interface for the hot path
+// (cpp-code/solvers.hpp and rcpp-code/MultivarTV/src/solvers.hpp), implemented on the C ABI of
+// include/mvtv.h (libmvtv_b200.so, CUDA sm_100a).  Same function names, argument meaning and error
+// behaviour as upstream, so upstream's C++ tests read the same:
+//
+//   softthresh        cpp-code/solvers.hpp:22
+//   admm_update       cpp-code/solvers.hpp:85          (rcpp: solvers.hpp:100, in namespace mvtv::rcpp)
+//   mbs_one           cpp-code/solvers.hpp:89          (rcpp: solvers.hpp:104)
+//   mbs_predict, mse, mbs_mse   cpp-code/solvers.hpp:93-97
+//   create_mesh, create_deltas, nearest1   cpp-code/utils.hpp:59-70
+//
+// Upstream passes Armadillo types by value; Armadillo is not a dependency here: `mvtv::vec` / `mvtv::mat`
+// are minimal column-major containers with the few members the interface needs (n_rows, n_cols, memptr(),
+// operator()(i,j), fill()).  Where <armadillo> exists, arma::vec / arma::mat convert implicitly
+// (MVTV_WITH_ARMADILLO is set automatically).  There is no CPU fallback: all arithmetic happens on the GPU.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mvtv.h"
+
+#if !defined(MVTV_NO_ARMADILLO) && defined(__has_include)
+#if __has_include(<armadillo>)
+#include <armadillo>
+#define MVTV_WITH_ARMADILLO 1
+#endif
+#endif
+
+namespace mvtv {
+
+struct vec {
+  std::vector<double> mem;
+  vec() {}
+  explicit vec(size_t n) : mem(n) {}
+  vec(std::initializer_list<double> l) : mem(l) {}
+  vec(const std::vector<double> &v) : mem(v) {}
+#ifdef MVTV_WITH_ARMADILLO
+  vec(const arma::vec &a) : mem(a.begin(), a.end()) {}
+  operator arma::vec() const { return arma::vec(mem); }
+#endif
+  size_t size() const { return mem.size(); }
+  size_t n_rows_() const { return mem.size(); }
+  double *memptr() { return mem.data(); }
+  const double *memptr() const { return mem.data(); }
+  double &operator[](size_t i) { return mem[i]; }
+  double operator[](size_t i) const { return mem[i]; }
+  double &operator()(size_t i) { return mem[i]; }
+  double operator()(size_t i) const { return mem[i]; }
+  void fill(double v) { std::fill(mem.begin(), mem.end(), v); }
+};
+
+struct mat {  // column-major, like arma::mat
+  size_t n_rows = 0, n_cols = 0;
+  std::vector<double> mem;
+  mat() {}
+  mat(size_t r, size_t c) : n_rows(r), n_cols(c), mem(r * c) {}
+#ifdef MVTV_WITH_ARMADILLO
+  mat(const arma::mat &a) : n_rows(a.n_rows), n_cols(a.n_cols), mem(a.begin(), a.end()) {}
+  mat(const arma::fmat &a) : n_rows(a.n_rows), n_cols(a.n_cols), mem(a.begin(), a.end()) {}
+#endif
+  double &operator()(size_t i, size_t j) { return mem[i + j * n_rows]; }
+  double operator()(size_t i, size_t j) const { return mem[i + j * n_rows]; }
+  double *memptr() { return mem.data(); }
+  const double *memptr() const { return mem.data(); }
+};
+typedef mat MAT;  // cpp-code/solvers.hpp:12 (fmat upstream: knots are float-rounded by create_mesh below)
+
+inline void check(int code) {
+  if (code == MVTV_OK) return;
+  const std::string msg = mvtv_last_error();
+  if (code == MVTV_ERR_NOT_CONVERGED) throw std::invalid_argument("Failed to converge!");  // cpp-code/solvers.cpp:123
+  if (code == MVTV_ERR_DIM_MISMATCH) throw std::logic_error(msg);                          // arma size mismatch
+  throw std::runtime_error("mvtv error " + std::to_string(code) + ": " + msg);
+}
+
+// ---- utils.hpp -------------------------------------------------------------------------------------
+inline double prodd(const vec &a) {  // cpp-code/utils.cpp:24-30
+  double p = 1.0;
+  for (size_t i = 0; i < a.size(); ++i) p *= a[i];
+  return p;
+}
+
+// knots of create_mesh (cpp-code/utils.cpp:271-298): linspace(min+EPS, max+EPS, m_k) rounded to float
+// (rcpp variant: min-EPS, EPS=1e-4, double: rcpp utils.cpp:234-254)
+inline std::vector<std::vector<double>> mesh_axes(const mat &data, const vec &dims, bool rcpp = false) {
+  std::vector<std::vector<double>> axes(data.n_cols);
+  for (size_t k = 0; k < data.n_cols; ++k) {
+    double lo = std::numeric_limits<double>::infinity(), hi = -lo;
+    for (size_t i = 0; i < data.n_rows; ++i) {
+      lo = std::min(lo, data(i, k));
+      hi = std::max(hi, data(i, k));
+    }
+    const double eps = rcpp ? 0.0001 : 0.01;
+    const double a = rcpp ? lo - eps : lo + eps, b = hi + eps;
+    const size_t m = (size_t)dims[k];
+    axes[k].resize(m);
+    const double delta = m > 1 ? (b - a) / double(m - 1) : 0.0;
+    for (size_t j = 0; j + 1 < m; ++j) axes[k][j] = a + double(j) * delta;
+    axes[k][m - 1] = b;
+    if (!rcpp)
+      for (double &v : axes[k]) v = (double)(float)v;
+  }
+  return axes;
+}
+
+inline MAT mesh_from_axes(const std::vector<std::vector<double>> &axes) {
+  size_t N = 1;
+  for (auto &a : axes) N *= a.size();
+  MAT mesh(N, axes.size());
+  size_t stride = 1;
+  for (size_t k = 0; k < axes.size(); ++k) {
+    for (size_t i = 0; i < N; ++i) mesh(i, k) = axes[k][(i / stride) % axes[k].size()];
+    stride *= axes[k].size();
+  }
+  return mesh;
+}
+
+inline MAT create_mesh(const mat &data, const vec &dims) { return mesh_from_axes(mesh_axes(data, dims)); }
+
+inline vec create_deltas(const mat &data, const vec &dims, double eps = 0.01) {  // cpp-code/utils.cpp:300-307
+  vec d(data.n_cols);
+  for (size_t k = 0; k < data.n_cols; ++k) {
+    double lo = std::numeric_limits<double>::infinity(), hi = -lo;
+    for (size_t i = 0; i < data.n_rows; ++i) {
+      lo = std::min(lo, data(i, k));
+      hi = std::max(hi, data(i, k));
+    }
+    d[k] = (hi - lo + 2 * eps) / dims[k];
+  }
+  return d;
+}
+
+// the tensor-product knots behind an N x p mesh matrix (the `MAT mesh` argument of mbs_one)
+inline std::vector<double> axes_of_mesh(const MAT &mesh, const vec &m) {
+  std::vector<double> axes;
+  size_t stride = 1;
+  for (size_t k = 0; k < m.size(); ++k) {
+    for (size_t j = 0; j < (size_t)m[k]; ++j) axes.push_back(mesh(j * stride, k));
+    stride *= (size_t)m[k];
+  }
+  return axes;
+}
+
+inline std::vector<long long> nearest1(const mat &data, const MAT &mesh, const vec &m) {  // cpp-code/utils.cpp:323-330
+  std::vector<int64_t> mm(m.size());
+  for (size_t k = 0; k < m.size(); ++k) mm[k] = (int64_t)m[k];
+  std::vector<double> axes = axes_of_mesh(mesh, m);
+  std::vector<int64_t> out(data.n_rows);
+  check(mvtv_nearest((int)m.size(), mm.data(), axes.data(), (int64_t)data.n_rows, data.memptr(), out.data()));
+  return std::vector<long long>(out.begin(), out.end());
+}
+
+// ---- solvers.hpp -----------------------------------------------------------------------------------
+inline vec softthresh(vec z, double lam) {  // cpp-code/solvers.hpp:22
+  vec out(z.size());
+  check(mvtv_softthresh((int64_t)z.size(), z.memptr(), lam, out.memptr()));
+  return out;
+}
+
+// mbs_cache (cpp-code/solvers.hpp:25-34): the operators O, D, Oty, crossO, crossD live on the device
+struct mbs_cache {
+  mvtv_plan *plan = nullptr;
+  int64_t ntheta = 0, rowsD = 0, n = 0;
+  std::vector<double> axes;
+  mbs_cache() {}
+  mbs_cache(const mbs_cache &) = delete;
+  mbs_cache &operator=(const mbs_cache &) = delete;
+  ~mbs_cache() {
+    if (plan) mvtv_plan_destroy(plan);
+  }
+};
+typedef mbs_cache mbs_one_inits;  // cpp-code/solvers.hpp:36-43: same objects, same owner here
+
+typedef struct mbs_one_object {  // cpp-code/solvers.hpp:45-52 (+ rhohat, uhat of rcpp solvers.hpp:52-61)
+  MAT mesh;
+  vec theta_hat;
+  vec fitted;
+  mat data;
+  vec y;
+  vec m;
+  double rhohat = 0.0;
+  vec uhat;
+  int counter = 0;
+} mbs_one_object;
+
+// create_cache_objects (cpp-code/solvers.cpp:31-41): O, D, crossD, crossO, Oty.  `deltas` empty = the
+// stand-alone mbs_one path (cpp-code/solvers.cpp:141-145).
+inline void create_cache_objects(const mat &data, const vec &y, const MAT &mesh, const vec &meshdims,
+                                 mbs_cache &inits, const vec &deltas = vec(), int dtype = MVTV_F64,
+                                 int variant = MVTV_VARIANT_REFERENCE) {
+  mvtv_plan_desc d{};
+  d.struct_size = (int32_t)sizeof(d);
+  d.p = (int32_t)meshdims.size();
+  for (size_t k = 0; k < meshdims.size() && k < MVTV_MAXP; ++k) d.m[k] = (int64_t)meshdims[k];
+  d.dtype = dtype;
+  d.variant = variant;
+  d.device = -1;
+  d.rank = 0;
+  d.world = 1;
+  d.deltas = deltas.size() ? deltas.memptr() : nullptr;
+  if (inits.plan) {
+    mvtv_plan_destroy(inits.plan);
+    inits.plan = nullptr;
+  }
+  check(mvtv_plan_create(&inits.plan, &d));
+  check(mvtv_plan_info(inits.plan, &inits.ntheta, &inits.rowsD, nullptr, nullptr));
+  inits.axes = axes_of_mesh(mesh, meshdims);
+  inits.n = (int64_t)data.n_rows;
+  check(mvtv_plan_set_points(inits.plan, inits.n, data.memptr(), y.memptr(), inits.axes.data()));
+}
+
+inline mvtv_solve_params default_params(int mode, double lambda) {
+  mvtv_solve_params p{};
+  p.struct_size = (int32_t)sizeof(p);
+  p.mode = mode;
+  p.lambda = lambda;
+  p.rho_init = p.rho_matrix0 = p.tol = std::numeric_limits<double>::quiet_NaN();
+  return p;
+}
+
+// admm_update (cpp-code/solvers.hpp:85): y is only used for mean(y), which the cache already holds.
+inline vec admm_update(const vec & /*y*/, mbs_cache &inits, vec *theta_init, double lambda, int *counter = nullptr) {
+  mvtv_solve_params p = default_params(MVTV_MODE_CPP, lambda);
+  mvtv_solve_result r{};
+  vec theta((size_t)inits.ntheta);
+  check(mvtv_solve(inits.plan, &p, theta_init ? theta_init->memptr() : nullptr, nullptr, theta.memptr(), nullptr, &r));
+  std::printf("Lambda = %f, Counter = %i \n", lambda, r.counter);  // cpp-code/solvers.cpp:128
+  if (counter) *counter = r.counter;
+  return theta;
+}
+
+// mbs_one (cpp-code/solvers.hpp:89)
+inline void mbs_one(const mat &data, const vec &y, const vec &m, mbs_one_object &output, const MAT &mesh,
+                    vec *theta_init = NULL, double lambda = 1.0, mbs_cache *cache = NULL) {
+  mbs_cache local;
+  mbs_cache *inits = cache;
+  if (cache == NULL) {  // cpp-code/solvers.cpp:141-145
+    create_cache_objects(data, y, mesh, m, local);
+    inits = &local;
+  }
+  mvtv_solve_params p = default_params(MVTV_MODE_CPP, lambda);
+  mvtv_solve_result r{};
+  output.theta_hat = vec((size_t)inits->ntheta);
+  output.fitted = vec((size_t)inits->n);
+  check(mvtv_solve(inits->plan, &p, theta_init ? theta_init->memptr() : nullptr, nullptr,
+                   output.theta_hat.memptr(), output.fitted.memptr(), &r));
+  std::printf("Lambda = %f, Counter = %i \n", lambda, r.counter);
+  output.mesh = mesh;  // fill_output_mbs_one, cpp-code/solvers.cpp:64-68
+  output.data = data;
+  output.y = y;
+  output.m = m;
+  output.rhohat = r.rho;
+  output.counter = r.counter;
+}
+
+inline vec mbs_predict(const mbs_one_object &model, const mat &data) {  // cpp-code/solvers.hpp:93
+  mbs_cache tmp;
+  mvtv_plan_desc d{};
+  d.struct_size = (int32_t)sizeof(d);
+  d.p = (int32_t)model.m.size();
+  for (size_t k = 0; k < model.m.size() && k < MVTV_MAXP; ++k) d.m[k] = (int64_t)model.m[k];
+  d.dtype = MVTV_F64;
+  d.device = -1;
+  d.world = 1;
+  check(mvtv_plan_create(&tmp.plan, &d));
+  std::vector<double> axes = axes_of_mesh(model.mesh, model.m);
+  vec fits(data.n_rows);
+  check(mvtv_predict(tmp.plan, (int64_t)data.n_rows, data.memptr(), axes.data(), model.theta_hat.memptr(), fits.memptr()));
+  return fits;
+}
+
+inline double mse(const vec &fits, const vec &y) {  // cpp-code/solvers.cpp:160-163
+  double s = 0.0;
+  for (size_t i = 0; i < y.size(); ++i) s += (fits[i] - y[i]) * (fits[i] - y[i]);
+  return s / double(y.size());
+}
+inline double mbs_mse(const mbs_one_object &model, const vec &y) { return mse(model.fitted, y); }
+
+// ---- rcpp-code/MultivarTV/src/solvers.hpp variants ---------------------------------------------------
+namespace rcpp {
+typedef struct admm_out {  // rcpp solvers.hpp:91-95
+  double rho;
+  vec theta;
+  vec u;
+} admm_out;
+
+// admm_update (rcpp solvers.hpp:100).  The first pass uses the cached matrix crossO + rho_init*crossD,
+// as mbs_path sets it (rcpp solvers.cpp:213); pass matrix_scalar to override (stand-alone mbs_one: lambda).
+inline void admm_update(const vec & /*y*/, mbs_cache &inits, vec &theta_init, double lambda, bool verbose, vec &u_init,
+                        double &rho_init, admm_out &out, double matrix_scalar = std::numeric_limits<double>::quiet_NaN(),
+                        int *counter = nullptr) {
+  mvtv_solve_params p = default_params(MVTV_MODE_RCPP, lambda);
+  p.rho_init = rho_init;
+  p.rho_matrix0 = (matrix_scalar == matrix_scalar) ? matrix_scalar : rho_init;
+  mvtv_solve_result r{};
+  out.theta = vec((size_t)inits.ntheta);
+  out.u = u_init;
+  const int code = mvtv_solve(inits.plan, &p, theta_init.memptr(), out.u.memptr(), out.theta.memptr(), nullptr, &r);
+  if (code == MVTV_ERR_NOT_CONVERGED)  // rcpp solvers.cpp:129-132: message + break
+    std::printf("ADMM reached max_counter at lambda = %g\n", lambda);
+  else
+    check(code);
+  if (verbose) std::printf("Lambda= %g, Counter = %d\n", lambda, r.counter);
+  out.rho = r.rho;
+  if (counter) *counter = r.counter;
+}
+
+// mbs_one (rcpp solvers.hpp:104)
+inline void mbs_one(const mat &data, const vec &y, const vec &m, mbs_one_object &output, const MAT &mesh, vec &u,
+                    double &rho, vec &theta_init, double lambda = 1.0, mbs_cache *cache = NULL, bool verbose = true) {
+  mbs_cache local;
+  mbs_cache *inits = cache;
+  double matrix_scalar = std::numeric_limits<double>::quiet_NaN();
+  if (cache == NULL) {  // rcpp solvers.cpp:147-151
+    create_cache_objects(data, y, mesh, m, local);
+    inits = &local;
+    matrix_scalar = lambda;
+  }
+  admm_out out;
+  int counter = 0;
+  admm_update(y, *inits, theta_init, lambda, verbose, u, rho, out, matrix_scalar, &counter);
+  output.mesh = mesh;  // fill_output_mbs_one, rcpp solvers.cpp:71-75
+  output.theta_hat = out.theta;
+  output.uhat = out.u;
+  output.rhohat = out.rho;
+  output.fitted = vec((size_t)inits->n);
+  check(mvtv_predict(inits->plan, inits->n, data.memptr(), inits->axes.data(), out.theta.memptr(), output.fitted.memptr()));
+  output.data = data;
+  output.y = y;
+  output.m = m;
+  output.counter = counter;
+}
+}  // namespace rcpp
+
+}  // namespace mvtv
