@@ -302,61 +302,58 @@ k_apply_M(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
 // ---------------------------------------------------------------------------------------------
 // k_cg_step: fused CG direction update + SpMV.
 //   p_new = dinv.*r + beta*p_old        (never re-read from HBM: built tile by tile in shared memory)
-//   q     = (diag(c) + rhoM*K) p_new    (3^P-point clamped stencil out of shared memory)
+//   q     = (diag(c) + rhoM*K) p_new    (3^P-point clamped stencil)
 //   p.q
 // A CTA owns an in-plane tile (TX x TY x TW over axes 0..Q-1, Q = P-1) and marches along the last axis
-// over a chunk of planes, keeping four rolling planes of p_new (tile + 1-deep halo) in shared memory:
-// one __syncthreads per plane.  Algorithmic traffic: read r, dinv, p_old, c ; write p_new, q  (6 N).
+// over a chunk of planes.
+//   * staging: the raw tiles (+ 1-deep halo, clamped at the mesh boundary) of r, dinv and p_old are
+//     copied global -> shared with cp.async (LDGSTS) into a DEPTH-stage ring, DEPTH-1 planes ahead of
+//     the consumer, so HBM latency is covered by the ring and not by occupancy;
+//   * combine: p_new of the plane is formed once in a shared tile and the owned part written back;
+//   * stencil: reuse along the marching axis happens in registers: when plane z arrives every thread
+//     adds its contribution to the three output planes z-1, z, z+1 (three running accumulator sets) and
+//     retires plane z-1.  In-plane a thread owns RY consecutive outputs along axis 1, so a (RY+2) x 3
+//     window feeds RY outputs and lanes run along axis 0 (conflict-free LDS).
+// Algorithmic traffic: read r, dinv, p_old, c ; write p_new, q  (6 N).
 // ---------------------------------------------------------------------------------------------
-template <int Q, int TX_, int TY_, int TW_, int NT_>
+template <int Q_, int TXT_, int XO_, int TY_, int RY_, int TW_, int DEPTH_>
 struct StepCfg {
-  static constexpr int TX = TX_, TY = TY_, TW = TW_, NT = NT_;
-  static constexpr int EX = TX + 2, EY = (Q >= 2 ? TY + 2 : 1), EW = (Q >= 3 ? TW + 2 : 1);
+  static constexpr int Q = Q_;
+  static constexpr int TXT = TXT_;          // threads along axis 0
+  static constexpr int XO = XO_;            // strided outputs per thread along axis 0
+  static constexpr int TX = TXT_ * XO_, TY = TY_, TW = TW_, RY = RY_;
+  static constexpr int NT = TXT_ * (TY_ / RY_) * TW_;
+  static constexpr int EX = TX + 2, EY = (Q_ >= 2 ? TY_ + 2 : 1), EW = (Q_ >= 3 ? TW_ + 2 : 1);
   static constexpr int TE = EX * EY * EW;   // plane tile with halo
-  static constexpr int TI = TX * TY * TW;   // outputs per plane
   static constexpr int NE = (TE + NT - 1) / NT;
-  static constexpr int NO = (TI + NT - 1) / NT;
-  static constexpr int SLOTS = 4;
+  static constexpr int DEPTH = DEPTH_;      // cp.async ring stages
+  static constexpr int SMEM_ELEMS = (3 * DEPTH_ + 1) * TE;
+  static_assert(TY_ % RY_ == 0, "RY must divide TY");
+  static_assert(Q_ >= 2 || (TY_ == 1 && RY_ == 1), "Q=1 has no axis 1");
+  static_assert(Q_ >= 3 || TW_ == 1, "Q<3 has no axis 2");
 };
 
-template <typename T, int Q, typename Cfg>
-__device__ __forceinline__ T stencil_smem(const T *sm, const T *s0, const T *sp, int e0, const StencilTab &st) {
-  constexpr int EX = Cfg::EX, EY = Cfg::EY;
-  T acc = 0;
-#pragma unroll
-  for (int dz = 0; dz < 3; ++dz) {
-    const T *s = (dz == 0) ? sm : ((dz == 1) ? s0 : sp);
-    if constexpr (Q == 1) {
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) acc += (T)st.coef[dz * 3 + dx] * s[e0 + dx - 1];
-    } else if constexpr (Q == 2) {
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
-          acc += (T)st.coef[(dz * 3 + dy) * 3 + dx] * s[e0 + (dy - 1) * EX + dx - 1];
-    } else {
-#pragma unroll
-      for (int dw = 0; dw < 3; ++dw)
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx)
-            acc += (T)st.coef[((dz * 3 + dw) * 3 + dy) * 3 + dx] * s[e0 + (dw - 1) * EX * EY + (dy - 1) * EX + dx - 1];
-    }
-  }
-  return acc;
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-template <typename T, int Q, typename Cfg>
+template <typename T, typename Cfg>
 __global__ void __launch_bounds__(Cfg::NT)
 k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
           const RedBuf rb, const int zchunk) {
   if (cg_done(a.S, a.rtol2)) return;
-  constexpr int TX = Cfg::TX, TY = Cfg::TY, TW = Cfg::TW, NT = Cfg::NT;
-  constexpr int EX = Cfg::EX, EY = Cfg::EY, TE = Cfg::TE, TI = Cfg::TI, NE = Cfg::NE, NO = Cfg::NO;
+  constexpr int Q = Cfg::Q, TXT = Cfg::TXT, XO = Cfg::XO, TX = Cfg::TX, TY = Cfg::TY, TW = Cfg::TW, RY = Cfg::RY;
+  constexpr int NT = Cfg::NT, EX = Cfg::EX, EY = Cfg::EY, TE = Cfg::TE, NE = Cfg::NE, DEPTH = Cfg::DEPTH;
+  constexpr int NDY = (Q >= 2) ? 3 : 1, NDW = (Q >= 3) ? 3 : 1;   // in-plane stencil extents beyond axis 0
+  constexpr int PW = 3 * NDY * NDW;                                 // stencil points per plane
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *sp = reinterpret_cast<T *>(smem_raw);  // [SLOTS][TE]
+  T *ring = reinterpret_cast<T *>(smem_raw);   // [DEPTH][3][TE]: r, dinv, p_old
+  T *pn = ring + 3 * DEPTH * TE;               // [TE]: p_new of the plane being consumed
 
   const int tid = threadIdx.x;
   const int it = (int)a.S[CS_ITERS];
@@ -367,6 +364,7 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   T *__restrict__ p_out = a.pbuf[cur ^ 1];
   const T *__restrict__ rr = a.r;
   const T *__restrict__ dinv = a.dinv;
+  const T rhoM = (T)a.rhoM;
 
   // in-plane tile origin
   const int m0 = (int)dt.m[0];
@@ -381,7 +379,7 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   const int bw = bid / nty;
   const int x0 = bx * TX, y0 = by * TY, w0 = bw * TW;
 
-  // loader bookkeeping: clamped in-plane source offset of each tile element this thread fills, and whether the
+  // staging bookkeeping: clamped in-plane source offset of each tile element this thread stages, and whether the
   // element is an interior one inside the mesh (those are the vertices whose p_new this CTA writes back)
   int src[NE];
   bool wr[NE];
@@ -404,55 +402,144 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   const int zc1 = min(zc0 + zchunk, dt.nz);
   const int zlo = dt.has_lo ? -1 : 0;          // lowest / highest local plane that holds real data
   const int zhi = dt.has_hi ? dt.nz : dt.nz - 1;
+  const int zfirst = zc0 - 1, zlast = zc1;     // planes consumed by this CTA
 
-  // fill slot (z & 3) with plane clamp(z); write p_new back for planes this CTA owns (plus the ghost planes,
-  // which the first / last chunk keep up to date redundantly so p never needs a halo exchange)
-  auto load_plane = [&](int z) {
-    const int zs = min(max(z, zlo), zhi);
-    const bool own = (z == zs) && ((z >= zc0 && z < zc1) || (z < 0 && zc0 == 0) || (z >= dt.nz && zc1 == dt.nz));
-    T *dst = sp + ((z + 4) & 3) * TE;
-    const long long pb = (long long)(zs + 1) * dt.plane;
+  // issue the async copies of plane zz (clamped) into ring stage (zz - zfirst) % DEPTH; always commits a group
+  auto stage_plane = [&](int zz) {
+    if (zz <= zlast) {
+      const int zs = min(max(zz, zlo), zhi);
+      const long long pb = (long long)(zs + 1) * dt.plane;
+      T *dst = ring + (size_t)((zz - zfirst) % DEPTH) * 3 * TE;
 #pragma unroll
-    for (int k = 0; k < NE; ++k) {
-      const int e = tid + k * NT;
-      if (e < TE) {
-        const long long idx = pb + src[k];
-        T pn = dinv[idx] * rr[idx];
-        if (!first) pn += beta * p_in[idx];
-        dst[e] = pn;
-        if (own && wr[k]) p_out[idx] = pn;
+      for (int k = 0; k < NE; ++k) {
+        const int e = tid + k * NT;
+        if (e < TE) {
+          const long long idx = pb + src[k];
+          cp_async<sizeof(T)>(dst + e, rr + idx);
+          cp_async<sizeof(T)>(dst + TE + e, dinv + idx);
+          if (!first) cp_async<sizeof(T)>(dst + 2 * TE + e, p_in + idx);
+        }
       }
+    }
+    cp_async_commit();
+  };
+
+  // this thread's outputs: x = tx + i*TXT (i < XO), y = yb*RY + j (j < RY), w = tw
+  const int tx = tid % TXT;
+  const int yb = (tid / TXT) % (TY / RY);
+  const int tw = tid / (TXT * (TY / RY));
+  T A0[XO][RY], A1[XO][RY], A2[XO][RY], pcp[XO][RY];
+  T cq0[XO][RY], cq1[XO][RY], cq2[XO][RY];   // diag(c) of the planes retiring now / next / after next
+  long long oidx[XO][RY];                    // in-plane offset of each output, -1 outside the mesh
+#pragma unroll
+  for (int i = 0; i < XO; ++i)
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      A0[i][j] = A1[i][j] = A2[i][j] = pcp[i][j] = T(0);
+      cq0[i][j] = cq1[i][j] = cq2[i][j] = T(0);
+      const int gx = x0 + tx + i * TXT, gy = y0 + yb * RY + j, gw = w0 + tw;
+      oidx[i][j] = (gx < m0 && gy < m1 && gw < m2) ? gx + (long long)m0 * (gy + (long long)m1 * gw) : -1;
+    }
+  // register prefetch of diag(c), two planes ahead of its use in the retire step
+  auto fetch_c = [&](int z, T (&dst)[XO][RY]) {
+    if (z >= zc0 && z < zc1) {
+      const long long pb = (long long)(z + 1) * dt.plane;
+#pragma unroll
+      for (int i = 0; i < XO; ++i)
+#pragma unroll
+        for (int j = 0; j < RY; ++j)
+          if (oidx[i][j] >= 0) dst[i][j] = a.c[pb + oidx[i][j]];
     }
   };
 
   double red[1] = {0.0};
-  load_plane(zc0 - 1);
-  load_plane(zc0);
-  for (int z = zc0; z < zc1; ++z) {
-    load_plane(z + 1);
-    __syncthreads();
-    const T *sm = sp + ((z + 3) & 3) * TE;
-    const T *s0 = sp + ((z + 4) & 3) * TE;
-    const T *s1 = sp + ((z + 5) & 3) * TE;
-    const long long pb = (long long)(z + 1) * dt.plane;
 #pragma unroll
-    for (int k = 0; k < NO; ++k) {
-      const int o = tid + k * NT;
-      if (o < TI) {
-        const int tx = o % TX, ty = (o / TX) % TY, tw = o / (TX * TY);
-        const int gx = x0 + tx, gy = y0 + ty, gw = w0 + tw;
-        if (gx < m0 && gy < m1 && gw < m2) {
-          const int e0 = (tx + 1) + EX * (((Q >= 2) ? ty + 1 : 0) + EY * ((Q >= 3) ? tw + 1 : 0));
-          const T kp = stencil_smem<T, Q, Cfg>(sm, s0, s1, e0, st);
-          const long long idx = pb + gx + (long long)m0 * (gy + (long long)m1 * gw);
-          const T pv = s0[e0];
-          const T qv = a.c[idx] * pv + (T)a.rhoM * kp;
-          a.q[idx] = qv;
-          red[0] += (double)pv * (double)qv;
+  for (int d = 0; d < DEPTH - 1; ++d) stage_plane(zfirst + d);
+  fetch_c(zc0, cq1);
+  for (int zz = zfirst; zz <= zlast; ++zz) {
+    stage_plane(zz + DEPTH - 1);
+    fetch_c(zz + 1, cq2);
+    cp_async_wait<DEPTH - 1>();   // this thread's copies of plane zz have landed
+    __syncthreads();              // ... and everybody else's; also: all threads are done reading pn (plane zz-1)
+    // ---- combine: p_new of plane zz, written back for planes this CTA owns (plus the ghost planes, which the
+    // first / last chunk keep up to date redundantly so p never needs a halo exchange)
+    {
+      const int zs = min(max(zz, zlo), zhi);
+      const bool own = (zz == zs) && ((zz >= zc0 && zz < zc1) || (zz < 0 && zc0 == 0) || (zz >= dt.nz && zc1 == dt.nz));
+      const long long pb = (long long)(zs + 1) * dt.plane;
+      const T *stg = ring + (size_t)((zz - zfirst) % DEPTH) * 3 * TE;
+#pragma unroll
+      for (int k = 0; k < NE; ++k) {
+        const int e = tid + k * NT;
+        if (e < TE) {
+          T v = stg[TE + e] * stg[e];
+          if (!first) v += beta * stg[2 * TE + e];
+          pn[e] = v;
+          if (own && wr[k]) p_out[pb + src[k]] = v;
         }
       }
     }
+    __syncthreads();
+    // ---- stencil contributions of plane zz to output planes zz+1 (A2), zz (A1), zz-1 (A0)
+    T pcc[XO][RY];
+#pragma unroll
+    for (int i = 0; i < XO; ++i) {
+      const int ex = tx + i * TXT + 1;
+#pragma unroll
+      for (int dw = 0; dw < NDW; ++dw) {
+        const int ew = (Q >= 3) ? tw + dw : 0;
+        constexpr int NR = (Q >= 2) ? RY + 2 : 1;
+        T W[NR][3];
+#pragma unroll
+        for (int rrow = 0; rrow < NR; ++rrow) {
+          const int ey = (Q >= 2) ? yb * RY + rrow : 0;
+          const T *row = pn + ex - 1 + EX * (ey + EY * ew);
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) W[rrow][dx] = row[dx];
+        }
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          if (dw == ((Q >= 3) ? 1 : 0)) pcc[i][j] = W[(Q >= 2) ? j + 1 : 0][1];
+#pragma unroll
+          for (int dy = 0; dy < NDY; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const T w = W[(Q >= 2) ? j + dy : 0][dx];
+              const int ci = dx + 3 * (((Q >= 2) ? dy : 0) + NDY * ((Q >= 3) ? dw : 0));  // in-plane coefficient index
+              A2[i][j] += (T)st.coef[ci] * w;            // plane zz is the z-1 neighbour of output plane zz+1
+              A1[i][j] += (T)st.coef[ci + PW] * w;       // ... the centre plane of output plane zz
+              A0[i][j] += (T)st.coef[ci + 2 * PW] * w;   // ... the z+1 neighbour of output plane zz-1
+            }
+        }
+      }
+    }
+    // ---- retire output plane zz-1
+    if (zz - 1 >= zc0) {
+      const long long pb = (long long)zz * dt.plane;   // local plane zz-1 sits at (zz-1+1)*plane
+#pragma unroll
+      for (int i = 0; i < XO; ++i)
+#pragma unroll
+        for (int j = 0; j < RY; ++j)
+          if (oidx[i][j] >= 0) {
+            const T pv = pcp[i][j];
+            const T qv = cq0[i][j] * pv + rhoM * A0[i][j];
+            a.q[pb + oidx[i][j]] = qv;
+            red[0] += (double)pv * (double)qv;
+          }
+    }
+#pragma unroll
+    for (int i = 0; i < XO; ++i)
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        A0[i][j] = A1[i][j];
+        A1[i][j] = A2[i][j];
+        A2[i][j] = T(0);
+        pcp[i][j] = pcc[i][j];
+        cq0[i][j] = cq1[i][j];
+        cq1[i][j] = cq2[i][j];
+      }
   }
+  cp_async_wait<0>();
   double *dstp = a.raw ? a.raw : (a.S + CS_PQ);
   grid_reduce<1, 1>(red, rb, [dstp](const double (&res)[1]) { dstp[0] = res[0]; });
 }

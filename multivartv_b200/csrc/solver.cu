@@ -493,9 +493,10 @@ void mvtv_plan::launch_zu(double kappa, double usc, int mode, int init, bool wit
 
 // tile shapes of k_cg_step per mesh rank (in-plane tile x planes marched by one CTA)
 template <int P> struct StepShape;
-template <> struct StepShape<2> { using Cfg = StepCfg<1, 512, 1, 1, 256>; };
-template <> struct StepShape<3> { using Cfg = StepCfg<2, 64, 16, 1, 256>; };
-template <> struct StepShape<4> { using Cfg = StepCfg<3, 32, 8, 4, 256>; };
+//                                                  Q  TXT XO  TY RY TW DEPTH
+template <> struct StepShape<2> { using Cfg = StepCfg<1, 256, 2,  1, 1, 1, 4>; };   // 512-wide rows, 256 threads, 53 KB
+template <> struct StepShape<3> { using Cfg = StepCfg<2,  32, 1, 16, 4, 1, 4>; };   // 32x16 tile, 128 threads, 64 KB
+template <> struct StepShape<4> { using Cfg = StepCfg<3,  32, 1,  8, 2, 4, 3>; };   // 32x8x4 tile, 512 threads, 163 KB
 
 template <typename T, int P>
 int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, long long &inner, int &status) {
@@ -540,17 +541,34 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   const int m0 = (int)dt.m[0], m1 = Q >= 2 ? (int)dt.m[1] : 1, m2 = Q >= 3 ? (int)dt.m[2] : 1;
   const unsigned tiles = (unsigned)(((m0 + Cfg::TX - 1) / Cfg::TX) * ((m1 + Cfg::TY - 1) / Cfg::TY) *
                                     ((m2 + Cfg::TW - 1) / Cfg::TW));
-  int nchunk = (int)std::max<long long>(1, std::min<long long>(dt.nz, (148ll * 6 + tiles - 1) / tiles));
-  int zchunk = (dt.nz + nchunk - 1) / nchunk;
-  if (zchunk < 16) zchunk = std::min(16, dt.nz);   // keep the 2-plane prologue cheap
-  nchunk = (dt.nz + zchunk - 1) / zchunk;
-  const dim3 gs(tiles, (unsigned)nchunk, 1);
-  const size_t smem = sizeof(T) * (size_t)Cfg::SLOTS * Cfg::TE;
+  const size_t smem = sizeof(T) * (size_t)Cfg::SMEM_ELEMS;
   static bool attr_set = false;
+  static int occ = 1;
   if (!attr_set) {
-    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Q, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step<T, Cfg>, Cfg::NT, smem));
+    if (occ < 1) occ = 1;
     attr_set = true;
   }
+  // chunks of the marching axis: fill whole waves of (SMs x resident CTAs), keep chunks >= 16 planes so the
+  // two extra planes a chunk stages stay cheap
+  int nsm = 148;
+  MVTV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+  const long long slots = (long long)nsm * occ;
+  int nchunk = 1;
+  double best = -1.0;
+  const int maxchunk = std::max(1, std::min(dt.nz / 16, 256));
+  for (int nc = 1; nc <= maxchunk; ++nc) {
+    const int zc = (dt.nz + nc - 1) / nc;
+    const int ncr = (dt.nz + zc - 1) / zc;
+    const long long total = (long long)tiles * ncr;
+    const long long waves = (total + slots - 1) / slots;
+    const double eff = (double)total / (double)(waves * slots) * ((double)zc / (zc + 2.0));
+    if (eff > best + 1e-9) { best = eff; nchunk = ncr; }
+  }
+  int zchunk = (dt.nz + nchunk - 1) / nchunk;
+  nchunk = (dt.nz + zchunk - 1) / zchunk;
+  const dim3 gs(tiles, (unsigned)nchunk, 1);
   const int gu = (int)std::max<long long>(1, std::min<long long>(148 * 8, (dt.Nloc + 1023) / 1024));
   int launched = 0;
   int batch = std::max(2, std::min(last_cg_iters, 256));
@@ -559,7 +577,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     for (int k = 0; k < batch; ++k) {
       if (world > 1) exchange_ghosts<T>((T *)r);
       prof_begin(MVTV_KC_CG_STEP);
-      k_cg_step<T, Q, Cfg><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+      k_cg_step<T, Cfg><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       prof_end();
       if (world > 1) {
         allreduce(raw, 1, ncclSum);
