@@ -173,7 +173,9 @@ def run_ours(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     if rank == 0:
         mvbuild.build()
     if dist:
@@ -268,6 +270,9 @@ def run_ours(args):
                "call": "Plan.set_points(host x,y) + Plan.solve(%d passes, cold start) -> host theta, fitted" % re["passes"],
                "seconds": t_e2e, "passes": re["passes"]}
 
+    # every rank drops its plan (and NCCL communicator) at the same point: ncclCommDestroy is collective
+    Nl_, R_, Nfull_ = plan.n_local, plan.R, plan.N
+    plan.close()
     if rank != 0:
         if dist:
             dist.barrier()
@@ -276,7 +281,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
-    Nl, Rl = plan.n_local, plan.R * plan.n_local / max(1, plan.N)   # rows scale with the slab
+    Nl, Rl = Nl_, R_ * Nl_ / max(1, Nfull_)   # rows scale with the slab
     sb = stage_bytes(Nl, Rl, esz)
     performed = {"zu": passes, "cg_init": passes, "cg_step": inner, "cg_update": inner}
     stages = {}
@@ -313,7 +318,6 @@ def run_ours(args):
         cb = cpu_baseline(args, threads=0, passes=2)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
-    plan.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()

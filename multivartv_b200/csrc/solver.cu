@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -13,6 +14,7 @@
 
 #include "kernels.cuh"
 #include "setup.h"
+#include "zu_march.cuh"
 
 namespace mvtv {
 
@@ -129,6 +131,7 @@ struct mvtv_plan {
   size_t staging_bytes = 0;
   long long launches = 0;
   int last_cg_iters = 8;
+  int zu_variant = -1;   // ZV_* when the compile-time block tables of k_zu_march match this plan, else -1 (gather kernel)
 
   // optional per-kernel-class CUDA-event timing on the plan's stream (mvtv_plan_profile)
   bool prof_on = false;
@@ -271,6 +274,15 @@ struct mvtv_plan {
       off += rs;
     }
     rt.R = off;
+
+    // compile-time block tables of the marching z/u kernel: use it only if they agree with this plan's table
+    {
+      const int V = (p == 1) ? ZV_P1 : (variant == MVTV_VARIANT_REFERENCE ? ZV_REFERENCE : ZV_INTENDED);
+      bool same = (zu_num_blocks(P, V) == K);
+      for (int b = 0; same && b < K; ++b) same = (zu_block_mask(P, V, b) == bt.mask[b]);
+      const char *env = getenv("MVTV_ZU_KERNEL");
+      zu_variant = (same && !(env && std::string(env) == "gather")) ? V : -1;
+    }
 
     // 3^P-point stencil of D^T D = sum_b c_b^2 kron_{a in S'_b} L_a  (SURVEY A.6), clamped indices
     st.npts = 1;
@@ -420,6 +432,8 @@ struct mvtv_plan {
   int cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, long long &inner, int &status);
   template <typename T>
   void launch_zu(double kappa, double usc, int mode, int init, bool with_prev);
+  template <typename T, typename Cfg, int V>
+  void launch_zu_march(const ZuArgs<T> &a, const RedBuf &rb);
   template <typename T>
   int solve_t(const mvtv_solve_params &prm, const double *theta_init, double *u_inout, double *theta_out,
               double *fitted_out, mvtv_solve_result &res);
@@ -465,6 +479,41 @@ void mvtv_plan::sum_y(const double *y_dev, long long npts) {
   mean_y = h_scal[0] / cnt_total;
 }
 
+template <typename T, typename Cfg, int V>
+void mvtv_plan::launch_zu_march(const ZuArgs<T> &a, const RedBuf &rb) {
+  constexpr int Q = Cfg::Q;
+  const size_t smem = sizeof(T) * (size_t)Cfg::SMEM_ELEMS;
+  static bool attr_set = false;
+  static int occ = 1;
+  if (!attr_set) {
+    MVTV_CUDA(cudaFuncSetAttribute(k_zu_march<T, Cfg, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_zu_march<T, Cfg, V>, Cfg::NT, smem));
+    if (occ < 1) occ = 1;
+    attr_set = true;
+  }
+  const int m0 = (int)dt.m[0], m1 = Q >= 2 ? (int)dt.m[1] : 1, m2 = Q >= 3 ? (int)dt.m[2] : 1;
+  const long long tiles = (long long)((m0 + Cfg::OX - 1) / Cfg::OX) * ((m1 + Cfg::OY - 1) / Cfg::OY) *
+                          ((m2 + Cfg::OW - 1) / Cfg::OW);
+  int nsm = 148;
+  MVTV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+  const long long slots = (long long)nsm * occ;
+  int nchunk = 1;
+  double best = -1.0;
+  const int maxchunk = std::max(1, std::min(dt.nz / 16, 256));
+  for (int nc = 1; nc <= maxchunk; ++nc) {
+    const int zc = (dt.nz + nc - 1) / nc;
+    const int ncr = (dt.nz + zc - 1) / zc;
+    const long long total = tiles * ncr;
+    if (total > (1ll << 16)) break;
+    const long long waves = (total + slots - 1) / slots;
+    const double eff = (double)total / (double)(waves * slots) * ((double)zc / (zc + 1.0));
+    if (eff > best + 1e-9) { best = eff; nchunk = ncr; }
+  }
+  const int zchunk = (dt.nz + nchunk - 1) / nchunk;
+  nchunk = (dt.nz + zchunk - 1) / zchunk;
+  k_zu_march<T, Cfg, V><<<dim3((unsigned)tiles, (unsigned)nchunk, 1), Cfg::NT, smem, stream>>>(dt, bt, a, rb, zchunk);
+}
+
 template <typename T>
 void mvtv_plan::launch_zu(double kappa, double usc, int mode, int init, bool with_prev) {
   ZuArgs<T> a;
@@ -481,7 +530,20 @@ void mvtv_plan::launch_zu(double kappa, double usc, int mode, int init, bool wit
   a.red_out = zr;
   RedBuf rb{partials, counters + 0};
   prof_begin(init ? MVTV_KC_ZU_INIT : MVTV_KC_ZU);
-  k_zu<T><<<grid, block, 0, stream>>>(dt, bt, a, rb);
+  bool done = false;
+  if (zu_variant >= 0) {
+    switch (dt.P * 4 + zu_variant) {
+      case 2 * 4 + ZV_REFERENCE: launch_zu_march<T, ZuCfg<2, 256, 1, 1>, ZV_REFERENCE>(a, rb); done = true; break;
+      case 2 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<2, 256, 1, 1>, ZV_INTENDED>(a, rb); done = true; break;
+      case 2 * 4 + ZV_P1: launch_zu_march<T, ZuCfg<2, 256, 1, 1>, ZV_P1>(a, rb); done = true; break;
+      case 3 * 4 + ZV_REFERENCE: launch_zu_march<T, ZuCfg<3, 32, 16, 1>, ZV_REFERENCE>(a, rb); done = true; break;
+      case 3 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<3, 32, 16, 1>, ZV_INTENDED>(a, rb); done = true; break;
+      case 4 * 4 + ZV_REFERENCE: launch_zu_march<T, ZuCfg<4, 16, 8, 4>, ZV_REFERENCE>(a, rb); done = true; break;
+      case 4 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<4, 16, 8, 4>, ZV_INTENDED>(a, rb); done = true; break;
+      default: break;
+    }
+  }
+  if (!done) k_zu<T><<<grid, block, 0, stream>>>(dt, bt, a, rb);
   prof_end();
   MVTV_CUDA(cudaGetLastError());
   launches += 1;
