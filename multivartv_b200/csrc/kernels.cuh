@@ -198,6 +198,74 @@ __device__ __forceinline__ int neighbour_offsets(const DimTab &dt, long long q, 
   return cls;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-memory collectives for the CG loop (one process per GPU, buffers shared with CUDA IPC over
+// NVLink/NVSwitch).  Instead of launching NCCL kernels between the compute kernels, the reducing kernel's
+// last thread stores its partial sums straight into every peer's slot and raises a flag; the consumer sums
+// the world's partials in rank order (bitwise identical on every rank).  The kernel that produces r also
+// stores its boundary planes into the neighbours' ghost planes, so the CG iteration needs no NCCL call.
+// ---------------------------------------------------------------------------------------------
+#define MVTV_PEER_MAXW 8
+#define MVTV_PEER_NSLOT 4
+#define MVTV_PEER_NVAL 4
+struct PeerTab {
+  int rank, world, has_lo, has_hi;
+  double *slots[MVTV_PEER_MAXW];              // peer j's reduction slots  [NSLOT][MAXW][NVAL]
+  unsigned long long *flags[MVTV_PEER_MAXW];  // peer j's arrival flags    [NSLOT][MAXW]
+  unsigned long long *hflag_at_prev, *hflag_at_next;      // halo-ready flags we RAISE in the neighbours' buffers
+  unsigned long long *hflag_from_prev, *hflag_from_next;  // ... and the ones we WAIT on in our own buffer
+  void *rghost_at_prev, *rghost_at_next;      // the neighbours' ghost planes of r that this rank fills
+  int *error;                                 // set when a wait times out (a peer died): results become NaN
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(double *p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// returns false on timeout (~10 s): never hang the GPU on a dead peer
+__device__ __forceinline__ bool peer_spin(const unsigned long long *flag, unsigned long long seq, int *error) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < seq) {
+    if (clock64() - t0 > 20000000000ll) {
+      if (error) *error = 1;
+      return false;
+    }
+  }
+  return true;
+}
+// single thread: publish n partial values of reduction event `seq` to every rank (self included)
+__device__ __forceinline__ void peer_post(const PeerTab &pt, unsigned long long seq, const double *v, int n) {
+  const int slot = (int)(seq % MVTV_PEER_NSLOT);
+  for (int j = 0; j < pt.world; ++j)
+    for (int k = 0; k < n; ++k) st_relaxed_sys(pt.slots[j] + (slot * MVTV_PEER_MAXW + pt.rank) * MVTV_PEER_NVAL + k, v[k]);
+  __threadfence_system();
+  for (int j = 0; j < pt.world; ++j) st_release_sys(pt.flags[j] + slot * MVTV_PEER_MAXW + pt.rank, seq);
+}
+// single thread: wait for every rank's partials of event `seq`, add them in rank order
+__device__ __forceinline__ void peer_wait_sum(const PeerTab &pt, unsigned long long seq, double *out, int n) {
+  const int slot = (int)(seq % MVTV_PEER_NSLOT);
+  for (int k = 0; k < n; ++k) out[k] = 0.0;
+  bool ok = true;
+  for (int j = 0; j < pt.world; ++j) {
+    ok = peer_spin(pt.flags[pt.rank] + slot * MVTV_PEER_MAXW + j, seq, pt.error) && ok;
+    for (int k = 0; k < n; ++k) out[k] += ld_relaxed_sys(pt.slots[pt.rank] + (slot * MVTV_PEER_MAXW + j) * MVTV_PEER_NVAL + k);
+  }
+  if (!ok)
+    for (int k = 0; k < n; ++k) out[k] = nan("");
+}
+
 template <typename T>
 struct CgArgs {
   T *x;            // theta (ghosted slab), updated in place
@@ -214,6 +282,9 @@ struct CgArgs {
   double uscale;   // lazy rescale of u: b = Oty + rho*(v1 + uscale*v2)
   double rhoM;     // scalar of the system matrix diag(c) + rhoM * D^T D
   double rtol2;    // cg_rtol^2
+  const PeerTab *peer;          // non-null: peer-memory collectives (world > 1, CUDA IPC available)
+  unsigned long long seq_red;   // reduction event id this launch posts / commits
+  unsigned long long seq_halo;  // version of r's ghost planes this launch posts (init, update) or needs (step)
 };
 
 __device__ __forceinline__ bool cg_done(const double *S, double rtol2) {
@@ -271,13 +342,24 @@ k_cg_init(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
     const T zv = rv * a.dinv[base];
     a.r[base] = rv;
     a.xold[base] = xv;
+    if (a.peer) {  // fill the neighbours' ghost planes of r
+      if (zl == 0 && a.peer->has_lo) { ((T *)a.peer->rghost_at_prev)[q] = rv; __threadfence_system(); }
+      if (zl == dt.nz - 1 && a.peer->has_hi) { ((T *)a.peer->rghost_at_next)[q] = rv; __threadfence_system(); }
+    }
     red[0] = (double)rv * (double)zv;
     red[1] = (double)rv * (double)rv;
     red[2] = (double)bv * (double)bv;
   }
   double *S = a.S, *raw = a.raw;
-  grid_reduce<3, 3>(red, rb, [S, raw](const double (&res)[3]) {
-    if (raw) { raw[0] = res[0]; raw[1] = res[1]; raw[2] = res[2]; }
+  const PeerTab *peer = a.peer;
+  const unsigned long long sr = a.seq_red, sh = a.seq_halo;
+  grid_reduce<3, 3>(red, rb, [S, raw, peer, sr, sh](const double (&res)[3]) {
+    if (peer) {
+      __threadfence_system();
+      if (peer->has_lo) st_release_sys(peer->hflag_at_prev, sh);
+      if (peer->has_hi) st_release_sys(peer->hflag_at_next, sh);
+      peer_post(*peer, sr, res, 3);
+    } else if (raw) { raw[0] = res[0]; raw[1] = res[1]; raw[2] = res[2]; }
     else cg_commit_init(S, res);
   });
 }
@@ -403,6 +485,13 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   const int zlo = dt.has_lo ? -1 : 0;          // lowest / highest local plane that holds real data
   const int zhi = dt.has_hi ? dt.nz : dt.nz - 1;
   const int zfirst = zc0 - 1, zlast = zc1;     // planes consumed by this CTA
+  if (a.peer) {  // the neighbours fill our ghost planes of r directly: wait for the version this iteration needs
+    if (tid == 0) {
+      if (zc0 == 0 && dt.has_lo) peer_spin(a.peer->hflag_from_prev, a.seq_halo, a.peer->error);
+      if (zc1 == dt.nz && dt.has_hi) peer_spin(a.peer->hflag_from_next, a.seq_halo, a.peer->error);
+    }
+    __syncthreads();
+  }
 
   // issue the async copies of plane zz (clamped) into ring stage (zz - zfirst) % DEPTH; always commits a group
   auto stage_plane = [&](int zz) {
@@ -541,7 +630,12 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   }
   cp_async_wait<0>();
   double *dstp = a.raw ? a.raw : (a.S + CS_PQ);
-  grid_reduce<1, 1>(red, rb, [dstp](const double (&res)[1]) { dstp[0] = res[0]; });
+  const PeerTab *peer = a.peer;
+  const unsigned long long sr = a.seq_red;
+  grid_reduce<1, 1>(red, rb, [dstp, peer, sr](const double (&res)[1]) {
+    if (peer) peer_post(*peer, sr, res, 1);
+    else dstp[0] = res[0];
+  });
 }
 
 // theta += alpha p ; r -= alpha q ; r.z ; r.r     (flat streaming kernel over the owned slab)
@@ -549,6 +643,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_cg_update(const CgArgs<T> a, const long long plane, const long long nloc, const RedBuf rb) {
   if (cg_done(a.S, a.rtol2)) return;
+  T *gprev = (a.peer && a.peer->has_lo) ? (T *)a.peer->rghost_at_prev : nullptr;
+  T *gnext = (a.peer && a.peer->has_hi) ? (T *)a.peer->rghost_at_next : nullptr;
+  bool stored_peer = false;
   const int cur = ((int)a.S[CS_ITERS]) & 1;
   const T alpha = (T)(a.S[2 * cur] / a.S[CS_PQ]);
   const T *__restrict__ p = a.pbuf[cur ^ 1] + plane;
@@ -572,6 +669,8 @@ k_cg_update(const CgArgs<T> a, const long long plane, const long long nloc, cons
       const T rn = rv[k] - alpha * qv[k];
       x[j] = xv[k] + alpha * pv[k];
       r[j] = rn;
+      if (gprev && j < plane) { gprev[j] = rn; stored_peer = true; }
+      if (gnext && j >= nloc - plane) { gnext[j - (nloc - plane)] = rn; stored_peer = true; }
       red[0] += (double)rn * (double)(rn * dv[k]);
       red[1] += (double)rn * (double)rn;
     }
@@ -580,14 +679,43 @@ k_cg_update(const CgArgs<T> a, const long long plane, const long long nloc, cons
     const T rn = r[i] - alpha * q[i];
     x[i] += alpha * p[i];
     r[i] = rn;
+    if (gprev && i < plane) { gprev[i] = rn; stored_peer = true; }
+    if (gnext && i >= nloc - plane) { gnext[i - (nloc - plane)] = rn; stored_peer = true; }
     red[0] += (double)rn * (double)(rn * dinv[i]);
     red[1] += (double)rn * (double)rn;
   }
+  if (stored_peer) __threadfence_system();
   double *S = a.S, *raw = a.raw;
-  grid_reduce<2, 2>(red, rb, [S, raw](const double (&res)[2]) {
-    if (raw) { raw[0] = res[0]; raw[1] = res[1]; }
+  const PeerTab *peer = a.peer;
+  const unsigned long long sr = a.seq_red, sh = a.seq_halo;
+  grid_reduce<2, 2>(red, rb, [S, raw, peer, sr, sh](const double (&res)[2]) {
+    if (peer) {
+      __threadfence_system();
+      if (peer->has_lo) st_release_sys(peer->hflag_at_prev, sh);
+      if (peer->has_hi) st_release_sys(peer->hflag_at_next, sh);
+      peer_post(*peer, sr, res, 2);
+    } else if (raw) { raw[0] = res[0]; raw[1] = res[1]; }
     else cg_commit_update(S, res);
   });
+}
+
+// multi-GPU commits over peer memory: wait for the world's partials of the event, sum in rank order
+__global__ void k_cg_peer_commit_init(double *S, const PeerTab *peer, unsigned long long seq) {
+  double v[3];
+  peer_wait_sum(*peer, seq, v, 3);
+  cg_commit_init(S, v);
+}
+__global__ void k_cg_peer_commit_pq(double *S, const PeerTab *peer, unsigned long long seq, double rtol2) {
+  if (cg_done(S, rtol2)) return;
+  double v[1];
+  peer_wait_sum(*peer, seq, v, 1);
+  S[CS_PQ] = v[0];
+}
+__global__ void k_cg_peer_commit_update(double *S, const PeerTab *peer, unsigned long long seq, double rtol2) {
+  if (cg_done(S, rtol2)) return;
+  double v[2];
+  peer_wait_sum(*peer, seq, v, 2);
+  cg_commit_update(S, v);
 }
 
 // multi-GPU commits (after the all-reduce of `raw`)

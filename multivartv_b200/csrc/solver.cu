@@ -31,6 +31,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -52,6 +53,7 @@ struct NcclApi {
     MVTV_SYM(CommDestroy, "ncclCommDestroy");
     MVTV_SYM(GetUniqueId, "ncclGetUniqueId");
     MVTV_SYM(AllReduce, "ncclAllReduce");
+    MVTV_SYM(AllGather, "ncclAllGather");
     MVTV_SYM(Send, "ncclSend");
     MVTV_SYM(Recv, "ncclRecv");
     MVTV_SYM(GroupStart, "ncclGroupStart");
@@ -131,6 +133,11 @@ struct mvtv_plan {
   size_t staging_bytes = 0;
   long long launches = 0;
   int last_cg_iters = 8;
+  // peer-memory collectives of the CG loop (CUDA IPC); falls back to NCCL when unavailable or MVTV_COMM=nccl
+  unsigned char *cb = nullptr;          // this rank's comm buffer (slots, flags, halo flags, error word)
+  PeerTab *d_peer = nullptr;            // device copy of the peer table, nullptr = NCCL path
+  std::vector<void *> ipc_opened;
+  unsigned long long red_seq = 0, halo_seq = 0;
   int zu_variant = -1;   // ZV_* when the compile-time block tables of k_zu_march match this plan, else -1 (gather kernel)
 
   // optional per-kernel-class CUDA-event timing on the plan's stream (mvtv_plan_profile)
@@ -186,6 +193,17 @@ struct mvtv_plan {
 
   ~mvtv_plan() {
     cudaSetDevice(device);
+    cudaDeviceSynchronize();
+    for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
+    if (comm && world > 1 && !ipc_opened.empty()) {  // nobody frees a buffer a peer still maps
+      double *tmp = raw;
+      if (tmp && g_nccl.AllReduce) {
+        g_nccl.AllReduce(tmp, tmp, 1, ncclFloat64, ncclSum, comm, stream);
+        cudaStreamSynchronize(stream);
+      }
+    }
+    if (cb) cudaFree(cb);
+    if (d_peer) cudaFree(d_peer);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pbuf[0], pbuf[1], q, dinv, u[0], u[1], S, zr, raw, partials, counters, vid, staging};
     for (void *b : bufs)
@@ -375,6 +393,78 @@ struct mvtv_plan {
   void allreduce(double *buf, int n, ncclRedOp_t op) {
     if (world == 1) return;
     MVTV_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat64, op, comm, stream));
+  }
+
+  // Share the comm buffer and r with the other ranks through CUDA IPC and build the device peer table.
+  void setup_peer() {
+    const char *env = getenv("MVTV_COMM");
+    if (world < 2 || world > MVTV_PEER_MAXW || (env && std::string(env) == "nccl")) return;
+    const size_t n_slots = (size_t)MVTV_PEER_NSLOT * MVTV_PEER_MAXW * MVTV_PEER_NVAL;   // doubles
+    const size_t n_flags = (size_t)MVTV_PEER_NSLOT * MVTV_PEER_MAXW;                    // u64
+    const size_t cb_bytes = 8 * (n_slots + n_flags + 2 + 1);
+    MVTV_CUDA(cudaMalloc(&cb, cb_bytes));
+    MVTV_CUDA(cudaMemset(cb, 0, cb_bytes));
+    struct Handles { cudaIpcMemHandle_t cb, r; };
+    static_assert(sizeof(Handles) == 128, "two 64-byte IPC handles");
+    Handles mine;
+    bool ok = cudaIpcGetMemHandle(&mine.cb, cb) == cudaSuccess && cudaIpcGetMemHandle(&mine.r, r) == cudaSuccess;
+    // all ranks must take the same decision: all-reduce the ok flag with the handles' exchange
+    unsigned char *d_h = nullptr;
+    MVTV_CUDA(cudaMalloc(&d_h, sizeof(Handles) * world + 8));
+    std::vector<Handles> all(world);
+    MVTV_CUDA(cudaMemcpy(d_h + sizeof(Handles) * rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
+    MVTV_NCCL(g_nccl.AllGather(d_h + sizeof(Handles) * rank, d_h, sizeof(Handles), ncclChar, comm, stream));
+    MVTV_CUDA(cudaStreamSynchronize(stream));
+    MVTV_CUDA(cudaMemcpy(all.data(), d_h, sizeof(Handles) * world, cudaMemcpyDeviceToHost));
+    std::vector<unsigned char *> pcb(world, nullptr);
+    unsigned char *r_prev = nullptr, *r_next = nullptr;
+    for (int j = 0; ok && j < world; ++j) {
+      if (j == rank) { pcb[j] = cb; continue; }
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[j].cb, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+      ipc_opened.push_back(p);
+      pcb[j] = (unsigned char *)p;
+      if (j == rank - 1 || j == rank + 1) {
+        void *pr = nullptr;
+        if (cudaIpcOpenMemHandle(&pr, all[j].r, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+        ipc_opened.push_back(pr);
+        (j == rank - 1 ? r_prev : r_next) = (unsigned char *)pr;
+      }
+    }
+    cudaGetLastError();
+    double flag = ok ? 0.0 : 1.0;   // anybody failed -> everybody uses NCCL
+    MVTV_CUDA(cudaMemcpy(d_h, &flag, 8, cudaMemcpyHostToDevice));
+    MVTV_NCCL(g_nccl.AllReduce(d_h, d_h, 1, ncclFloat64, ncclSum, comm, stream));
+    MVTV_CUDA(cudaStreamSynchronize(stream));
+    MVTV_CUDA(cudaMemcpy(&flag, d_h, 8, cudaMemcpyDeviceToHost));
+    MVTV_CUDA(cudaFree(d_h));
+    if (flag != 0.0) {
+      for (void *p : ipc_opened) cudaIpcCloseMemHandle(p);
+      ipc_opened.clear();
+      return;
+    }
+    PeerTab pt{};
+    pt.rank = rank;
+    pt.world = world;
+    pt.has_lo = dt.has_lo;
+    pt.has_hi = dt.has_hi;
+    auto slots_of = [&](unsigned char *b) { return (double *)b; };
+    auto flags_of = [&](unsigned char *b) { return (unsigned long long *)(b + 8 * n_slots); };
+    auto hflags_of = [&](unsigned char *b) { return (unsigned long long *)(b + 8 * (n_slots + n_flags)); };
+    for (int j = 0; j < world; ++j) { pt.slots[j] = slots_of(pcb[j]); pt.flags[j] = flags_of(pcb[j]); }
+    // hflags[0] = "my ghost plane BELOW was filled by the previous rank", hflags[1] = "... ABOVE by the next rank"
+    pt.hflag_from_prev = hflags_of(cb) + 0;
+    pt.hflag_from_next = hflags_of(cb) + 1;
+    pt.hflag_at_prev = dt.has_lo ? hflags_of(pcb[rank - 1]) + 1 : nullptr;
+    pt.hflag_at_next = dt.has_hi ? hflags_of(pcb[rank + 1]) + 0 : nullptr;
+    // the slab of rank j has its own nz; its ghost-above plane starts at (nz_j + 1) * plane
+    const long long mz = dt.m[dt.P - 1], basez = mz / world, extra = mz % world;
+    auto nz_of = [&](int j) { return basez + (j < extra ? 1 : 0); };
+    pt.rghost_at_prev = dt.has_lo ? (void *)(r_prev + esz() * (size_t)((nz_of(rank - 1) + 1) * dt.plane)) : nullptr;
+    pt.rghost_at_next = dt.has_hi ? (void *)r_next : nullptr;
+    pt.error = (int *)(cb + 8 * (n_slots + n_flags + 2));
+    MVTV_CUDA(cudaMalloc(&d_peer, sizeof(PeerTab)));
+    MVTV_CUDA(cudaMemcpy(d_peer, &pt, sizeof(PeerTab), cudaMemcpyHostToDevice));
   }
 
   // ---- points --------------------------------------------------------------------------------
@@ -583,18 +673,26 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   a.v1 = (const T *)v1;
   a.v2 = (const T *)v2;
   a.S = S;
-  a.raw = world > 1 ? raw : nullptr;
+  a.raw = (world > 1 && !d_peer) ? raw : nullptr;
+  a.peer = d_peer;
+  a.seq_red = 0;
+  a.seq_halo = 0;
   a.rho = rho;
   a.uscale = usc;
   a.rhoM = rhoM;
   a.rtol2 = rtol * rtol;
   const dim3 g = grid_owned();
+  a.seq_red = ++red_seq;
+  a.seq_halo = ++halo_seq;
   prof_begin(MVTV_KC_CG_INIT);
   k_cg_init<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1});
   prof_end();
   MVTV_CUDA(cudaGetLastError());
   launches += 1;
-  if (world > 1) {
+  if (d_peer) {
+    k_cg_peer_commit_init<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red);
+    launches += 1;
+  } else if (world > 1) {
     allreduce(raw, 3, ncclSum);
     k_cg_commit_init<<<1, 1, 0, stream>>>(S, raw);
     launches += 1;
@@ -637,18 +735,25 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   double iters = 0;
   for (;;) {
     for (int k = 0; k < batch; ++k) {
-      if (world > 1) exchange_ghosts<T>((T *)r);
+      if (world > 1 && !d_peer) exchange_ghosts<T>((T *)r);
+      a.seq_red = ++red_seq;       // a.seq_halo: the version the last producer of r posted
       prof_begin(MVTV_KC_CG_STEP);
       k_cg_step<T, Cfg><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       prof_end();
-      if (world > 1) {
+      if (d_peer) {
+        k_cg_peer_commit_pq<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
+      } else if (world > 1) {
         allreduce(raw, 1, ncclSum);
         k_cg_commit_pq<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
       }
+      a.seq_red = ++red_seq;
+      a.seq_halo = ++halo_seq;
       prof_begin(MVTV_KC_CG_UPDATE);
       k_cg_update<T><<<gu, 256, 0, stream>>>(a, dt.plane, dt.Nloc, RedBuf{partials, counters + 3});
       prof_end();
-      if (world > 1) {
+      if (d_peer) {
+        k_cg_peer_commit_update<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
+      } else if (world > 1) {
         allreduce(raw, 2, ncclSum);
         k_cg_commit_update<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
       }
@@ -915,6 +1020,7 @@ int mvtv_plan_create(mvtv_plan **out, const mvtv_plan_desc *d) {
       ncclUniqueId id;
       memcpy(&id, d->nccl_unique_id, sizeof(id));
       MVTV_NCCL(g_nccl.CommInitRank(&pl->comm, d->world, id, d->rank));
+      pl->setup_peer();
     }
     *out = pl.release();
     return MVTV_OK;
