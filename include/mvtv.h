@@ -157,6 +157,19 @@ int mvtv_plan_get_cache(mvtv_plan *plan, double *Oty, double *counts, int64_t *v
 int mvtv_solve(mvtv_plan *plan, const mvtv_solve_params *prm, const double *theta_init, double *u_inout,
                double *theta_out, double *fitted_out, mvtv_solve_result *res);
 
+/* Replaces: mbs_path (cpp-code/solvers.cpp:196-217 ; rcpp solvers.cpp:204-222): the lambdas are solved strictly in
+ * order, each warm-started from the previous one WITHOUT leaving the device (CPP/PY mode: theta carried, system
+ * matrix crossO + lambda_i*crossD; RCPP mode: theta, u and rho carried, first-pass matrix crossO + rho*crossD).
+ * prm->lambda is ignored.  ftrue: n doubles (pass y for the reference default, gen_ftrue solvers.cpp:235-244).
+ * mses_out[i] = mse(fitted_i, ftrue) (n_lambda doubles); counters_out (nullable); thetas_out (nullable,
+ * n_lambda x N); theta_best_out / fitted_best_out / best_index_out: the first lambda attaining the lowest MSE
+ * (fill_output_mbs, solvers.cpp:170-177).  total: passes, inner iterations, device seconds summed over the path.
+ * A CPP-mode non-convergence stops the path with MVTV_ERR_NOT_CONVERGED, like the uncaught throw upstream. */
+int mvtv_solve_path(mvtv_plan *plan, const mvtv_solve_params *prm, int32_t n_lambda, const double *lambdas,
+                    const double *ftrue, double *mses_out, int32_t *counters_out, double *thetas_out,
+                    double *theta_best_out, double *fitted_best_out, int32_t *best_index_out,
+                    mvtv_solve_result *total);
+
 /* Replaces: mbs_predict (cpp-code/solvers.hpp:93): nearest vertex of each new point, gather theta. */
 int mvtv_predict(mvtv_plan *plan, int64_t n_new, const double *data_colmajor, const double *axes,
                  const double *theta, double *fits_out);

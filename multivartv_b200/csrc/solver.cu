@@ -552,6 +552,19 @@ __global__ void __launch_bounds__(256) k_maxabs_const(const T *__restrict__ x_gh
   grid_reduce<1, 0>(red, rb, [out](const double (&res)[1]) { out[0] = res[0]; });
 }
 
+// sum_i (theta[vertex(i)] - target_i)^2 over this rank's points: the numerator of mse() (cpp-code/solvers.cpp:160-163)
+template <typename T>
+__global__ void __launch_bounds__(256) k_sqerr(const long long *__restrict__ vid, const T *__restrict__ theta_ghosted,
+                                               const double *__restrict__ target, long long n, long long plane,
+                                               long long z0, RedBuf rb, double *out) {
+  double red[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double d = (double)theta_ghosted[plane + (vid[i] - z0 * plane)] - target[i];
+    red[0] += d * d;
+  }
+  grid_reduce<1, 1>(red, rb, [out](const double (&res)[1]) { out[0] = res[0]; });
+}
+
 void mvtv_plan::sum_y(const double *y_dev, long long npts) {
   const int g = std::min<int>(grid1d(npts), (int)nblocks);
   RedBuf rb{partials, counters + 4};
@@ -1136,6 +1149,119 @@ int mvtv_solve(mvtv_plan *plan, const mvtv_solve_params *prm, const double *thet
     if (st == MVTV_ERR_NOT_CONVERGED) set_last_error("Failed to converge!");
     if (st == MVTV_ERR_INNER_SOLVE) set_last_error("x-update CG did not reach cg_rtol within cg_maxit");
     return st;
+  });
+}
+
+int mvtv_solve_path(mvtv_plan *plan, const mvtv_solve_params *prm, int32_t n_lambda, const double *lambdas,
+                    const double *ftrue, double *mses_out, int32_t *counters_out, double *thetas_out,
+                    double *theta_best_out, double *fitted_best_out, int32_t *best_index_out, mvtv_solve_result *total) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && prm && lambdas && ftrue && mses_out && total, "null argument");
+    MVTV_REQUIRE(prm->struct_size == (int32_t)sizeof(mvtv_solve_params), "mvtv_solve_params size mismatch");
+    MVTV_REQUIRE(n_lambda >= 1, "n_lambda must be >= 1");
+    MVTV_REQUIRE(plan->have_points, "call mvtv_plan_set_points first");
+    plan->use_device();
+    cudaStream_t s = plan->stream;
+    const long long n = plan->n, nl = plan->dt.Nloc;
+    double *d_target = nullptr;
+    MVTV_CUDA(cudaMalloc(&d_target, sizeof(double) * (size_t)n));
+    memset(total, 0, sizeof(*total));
+    int rc = MVTV_OK;
+    try {
+      MVTV_CUDA(cudaMemcpyAsync(d_target, ftrue, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+      mvtv_solve_params p = *prm;
+      double rho_carry = (p.rho_init == p.rho_init) ? p.rho_init : lambdas[0] / 5.0;  // rcpp solvers.cpp:209
+      int best = 0;
+      double best_mse = INFINITY;
+      std::vector<double> theta_tmp;
+      for (int i = 0; i < n_lambda; ++i) {
+        p.lambda = lambdas[i];
+        if (p.mode == MVTV_MODE_RCPP) {
+          // rcpp mbs_path (solvers.cpp:212-220): theta, u, rho carried; cached matrix = crossO + rho_init*crossD
+          p.rho_init = rho_carry;
+          p.rho_matrix0 = rho_carry;
+          p.flags = (i == 0) ? (prm->flags & ~(MVTV_WARM_THETA_FROM_PLAN | MVTV_WARM_U_FROM_PLAN))
+                             : (MVTV_WARM_THETA_FROM_PLAN | MVTV_WARM_U_FROM_PLAN);
+        } else {
+          // cpp mbs_path (solvers.cpp:207-214): theta carried, sp_crosses = crossO + lambda*crossD, u and rho restart
+          p.rho_matrix0 = lambdas[i];
+          p.flags = (i == 0) ? (prm->flags & ~MVTV_WARM_THETA_FROM_PLAN) : MVTV_WARM_THETA_FROM_PLAN;
+        }
+        mvtv_solve_result r;
+        memset(&r, 0, sizeof(r));
+        double *th_out = thetas_out ? thetas_out + (size_t)i * nl : nullptr;
+        int st;
+        if (plan->dtype == MVTV_F64) st = plan->solve_t<double>(p, nullptr, nullptr, th_out, nullptr, r);
+        else st = plan->solve_t<float>(p, nullptr, nullptr, th_out, nullptr, r);
+        if (st == MVTV_ERR_NOT_CONVERGED && p.mode != MVTV_MODE_RCPP) {  // cpp: the throw leaves mbs_path
+          set_last_error("Failed to converge!");
+          rc = st;
+          if (counters_out) counters_out[i] = r.counter;
+          break;
+        }
+        if (st != MVTV_OK && st != MVTV_ERR_NOT_CONVERGED) { rc = st; break; }
+        rho_carry = r.rho;
+        // MSEs[i] = mbs_mse(tempmodel, ftrue)  (cpp :212 / rcpp :216)
+        const int g = std::min<int>(mvtv_plan::grid1d(n), (int)plan->nblocks);
+        if (plan->dtype == MVTV_F64)
+          k_sqerr<double><<<g, 256, 0, s>>>(plan->vid, (const double *)plan->theta, d_target, n, plan->dt.plane,
+                                            plan->dt.z0, RedBuf{plan->partials, plan->counters + 4}, plan->zr);
+        else
+          k_sqerr<float><<<g, 256, 0, s>>>(plan->vid, (const float *)plan->theta, d_target, n, plan->dt.plane,
+                                           plan->dt.z0, RedBuf{plan->partials, plan->counters + 4}, plan->zr);
+        MVTV_CUDA(cudaGetLastError());
+        plan->launches += 1;
+        double cnt = (double)n;
+        if (plan->world > 1) {
+          MVTV_CUDA(cudaMemcpyAsync(plan->zr + 1, &cnt, sizeof(double), cudaMemcpyHostToDevice, s));
+          plan->allreduce(plan->zr, 2, ncclSum);
+        }
+        MVTV_CUDA(cudaMemcpyAsync(plan->h_scal, plan->zr, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+        MVTV_CUDA(cudaStreamSynchronize(s));
+        if (plan->world > 1) cnt = plan->h_scal[1];
+        const double m = plan->h_scal[0] / cnt;
+        mses_out[i] = m;
+        if (counters_out) counters_out[i] = r.counter;
+        if (m < best_mse) {  // first instance of the lowest MSE (cpp solvers.cpp:172-175)
+          best_mse = m;
+          best = i;
+          if (theta_best_out || fitted_best_out) {
+            theta_tmp.resize((size_t)nl);
+            double *stg = plan->stage(sizeof(double) * (size_t)std::max(nl, n));
+            if (plan->dtype == MVTV_F64) k_export<double><<<mvtv_plan::grid1d(nl), 256, 0, s>>>(stg, (const double *)plan->theta, plan->dt.plane, nl);
+            else k_export<float><<<mvtv_plan::grid1d(nl), 256, 0, s>>>(stg, (const float *)plan->theta, plan->dt.plane, nl);
+            MVTV_CUDA(cudaMemcpyAsync(theta_tmp.data(), stg, sizeof(double) * (size_t)nl, cudaMemcpyDeviceToHost, s));
+            MVTV_CUDA(cudaStreamSynchronize(s));
+          }
+        }
+        total->passes += r.passes;
+        total->counter += r.counter;
+        total->inner_iters += r.inner_iters;
+        total->device_seconds += r.device_seconds;
+        total->kernel_launches += r.kernel_launches;
+        total->rho = r.rho;
+        total->r_norm = r.r_norm;
+        total->s_norm = r.s_norm;
+        total->max_dtheta = r.max_dtheta;
+        if (st == MVTV_ERR_NOT_CONVERGED) total->status = st;
+      }
+      if (best_index_out) *best_index_out = best;
+      if (rc == MVTV_OK && theta_best_out) memcpy(theta_best_out, theta_tmp.data(), sizeof(double) * (size_t)nl);
+      if (rc == MVTV_OK && fitted_best_out) {
+        // fitted = O * theta_best through the predict gather on the staged copy
+        double *stg = plan->stage(sizeof(double) * (size_t)(plan->dt.usz + n));
+        MVTV_CUDA(cudaMemsetAsync(stg, 0, sizeof(double) * (size_t)plan->dt.usz, s));
+        MVTV_CUDA(cudaMemcpyAsync(stg + plan->dt.plane, theta_tmp.data(), sizeof(double) * (size_t)nl, cudaMemcpyHostToDevice, s));
+        launch_gather<double>(n, plan->vid, stg, plan->dt.plane, plan->dt.z0, plan->dt.nz, stg + plan->dt.usz, s);
+        MVTV_CUDA(cudaMemcpyAsync(fitted_best_out, stg + plan->dt.usz, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+        MVTV_CUDA(cudaStreamSynchronize(s));
+      }
+    } catch (...) {
+      cudaFree(d_target);
+      throw;
+    }
+    MVTV_CUDA(cudaFree(d_target));
+    return rc;
   });
 }
 

@@ -258,6 +258,39 @@ class Plan:
                     inner_iters=int(res.inner_iters), device_seconds=res.device_seconds,
                     kernel_launches=int(res.kernel_launches))
 
+    def solve_path(self, lambdas, ftrue, mode="cpp", tol=None, max_counter=0, cg_rtol=0.0, cg_maxit=0,
+                   rho_init=None, want_thetas=False, want_best=True):
+        """mbs_path (cpp-code/solvers.cpp:196-217 ; rcpp solvers.cpp:204-222): warm-started lambda path that stays
+        on the device between lambdas.  Returns MSEs, Counters and the first minimum-MSE model."""
+        L = _lib.load()
+        mode = _MODES[mode]
+        lambdas = _f64(np.asarray(lambdas).ravel())
+        ftrue = _f64(np.asarray(ftrue).ravel())
+        assert ftrue.size == self.n
+        prm = _lib.SolveParams()
+        prm.struct_size = C.sizeof(_lib.SolveParams)
+        prm.mode, prm.lam = mode, float(lambdas[0])
+        prm.rho_init = math.nan if rho_init is None else float(rho_init)
+        prm.rho_matrix0 = math.nan
+        prm.tol = math.nan if tol is None else float(tol)
+        prm.max_counter, prm.cg_rtol, prm.cg_maxit = int(max_counter), float(cg_rtol), int(cg_maxit)
+        nl = lambdas.size
+        mses = np.empty(nl)
+        counters = np.zeros(nl, dtype=np.int32)
+        thetas = np.empty((nl, self.n_local)) if want_thetas else None
+        tb = np.empty(self.n_local) if want_best else None
+        fb = np.empty(self.n) if want_best else None
+        best = C.c_int32(0)
+        res = _lib.SolveResult()
+        code = L.mvtv_solve_path(self._h, C.byref(prm), nl, _dp(lambdas), _dp(ftrue), _dp(mses),
+                                 counters.ctypes.data_as(C.POINTER(C.c_int32)), _dp(thetas), _dp(tb), _dp(fb),
+                                 C.byref(best), C.byref(res))
+        _lib.check(code)
+        return dict(mses=mses, counters=counters, thetas=thetas, theta_best=tb, fitted_best=fb, best_index=best.value,
+                    minmse=float(mses[best.value]), minmse_lambda=float(lambdas[best.value]), passes=res.passes,
+                    inner_iters=int(res.inner_iters), device_seconds=res.device_seconds, rho=res.rho,
+                    kernel_launches=int(res.kernel_launches), status=res.status)
+
     def predict(self, data, theta=None, axes=None):
         """mbs_predict (cpp-code/solvers.cpp:154-158)."""
         dcm, n, p = _colmajor(data)

@@ -302,3 +302,66 @@ def test_large_mesh_properties(mv):
         pl.set_points(x, np.full(n, 3.25), axes)
         out = pl.solve(50.0, mode="rcpp", max_passes=30)
         assert np.abs(out["theta"] - 3.25).max() <= 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# lambda path (BASELINE config 5): device-resident warm starts
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["cpp", "rcpp"])
+def test_lambda_path_parity(mv, mode):
+    """mbs_path (cpp-code/solvers.cpp:196-217 ; rcpp solvers.cpp:204-222) vs the oracle run lambda by lambda
+    with the same warm starts: identical Counters, MSEs and best index, theta within 1e-9."""
+    imode = {"cpp": 0, "rcpp": 1}[mode]
+    x, y = synth(5, 800, 2)
+    m = [14, 14]
+    axes = po.mesh_axes(x, m, imode)
+    lam_max = 6.0
+    lambdas = np.flipud(np.exp(np.linspace(np.log(lam_max * 1e-3), np.log(lam_max), 8)))   # cpp solvers.cpp:185
+    th = u = None
+    rho = lambdas[0] / 5.0
+    ref_mses, ref_counters, ref_thetas = [], [], []
+    for lam in lambdas:
+        if imode == 0:
+            r = co.mbs_one(x, y, m, axes, lam, mode=co.MODE_CPP, theta_init=th)
+        else:
+            r = co.mbs_one(x, y, m, axes, lam, mode=co.MODE_RCPP, theta_init=th, u_init=u, rho_init=rho, rho_matrix0=rho)
+            u, rho = r["u"], r["rho"]
+        th = r["theta"]
+        ref_mses.append(po.mse(r["fitted"], y))
+        ref_counters.append(r["counter"])
+        ref_thetas.append(r["theta"])
+    with mv.Plan(m) as pl:
+        pl.set_points(x, y, axes)
+        out = pl.solve_path(lambdas, y, mode=mode, want_thetas=True)
+    assert list(out["counters"]) == ref_counters
+    assert np.allclose(out["mses"], ref_mses, rtol=1e-9, atol=0)
+    best = int(np.flatnonzero(np.array(ref_mses) - np.min(ref_mses) == 0)[0])
+    assert out["best_index"] == best
+    for i in range(len(lambdas)):
+        assert np.abs(out["thetas"][i] - ref_thetas[i]).max() <= FP64_TOL
+    assert np.abs(out["theta_best"] - ref_thetas[best]).max() <= FP64_TOL
+
+
+def test_lambda_path_config5_shape(mv):
+    """BASELINE config 5 shape (32 warm-started lambdas on a 3-D mesh, reduced to 96^3 so the test stays short) in
+    CPP mode: the whole path runs without leaving the device; first and last lambda agree with stand-alone solves
+    given the same warm start."""
+    dims = [96, 96, 96]
+    N = int(np.prod(dims))
+    rng = np.random.RandomState(8)
+    x = rng.uniform(0, 1, (N, 3))
+    y = np.prod(x > 0.5, axis=1) * 1.0 + 0.5 * np.prod(x < 0.2, axis=1) + 0.5 * rng.normal(size=N)
+    axes = [np.linspace(0, 1, d) for d in dims]
+    lambdas = np.flipud(np.exp(np.linspace(np.log(3e-4), np.log(3.0), 32)))
+    with mv.Plan(dims) as pl:
+        pl.set_points(x, y, axes)
+        out = pl.solve_path(lambdas, y, mode="cpp", want_thetas=True)
+        assert np.all(out["counters"] >= 3) and np.all(out["counters"] <= 2000)
+        assert np.all(np.isfinite(out["mses"]))
+        first = pl.solve(lambdas[0], mode="cpp")
+        assert first["counter"] == out["counters"][0]
+        assert np.abs(first["theta"] - out["thetas"][0]).max() <= 1e-12
+        last = pl.solve(lambdas[-1], mode="cpp", theta_init=out["thetas"][-2])
+        assert last["counter"] == out["counters"][-1]
+        assert np.abs(last["theta"] - out["thetas"][-1]).max() <= 1e-12
+        assert out["minmse"] == out["mses"].min()
