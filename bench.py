@@ -255,6 +255,7 @@ def run_ours(args):
             dist.barrier()
         t0 = time.perf_counter()
         plan.set_points(x, y, axes)
+        t_sp = time.perf_counter() - t0
         re = plan.solve(args.lam, max_passes=args.steps, mode=mode, cg_rtol=args.cg_rtol, want_theta=True,
                         want_fitted=True, raise_on_nonconvergence=False)
         t_e2e = time.perf_counter() - t0
@@ -268,7 +269,8 @@ def run_ours(args):
         e2e = {"value": N * re["passes"] / t_e2e, "unit": "vertex-updates/s",
                "h2d_bytes_per_step": h2d / max(1, re["passes"]), "d2h_bytes_per_step": d2h / max(1, re["passes"]),
                "call": "Plan.set_points(host x,y) + Plan.solve(%d passes, cold start) -> host theta, fitted" % re["passes"],
-               "seconds": t_e2e, "passes": re["passes"]}
+               "seconds": t_e2e, "passes": re["passes"], "set_points_seconds": t_sp,
+               "solve_device_seconds": re["device_seconds"], "inner_cg_iters": re["inner_iters"]}
 
     # every rank drops its plan (and NCCL communicator) at the same point: ncclCommDestroy is collective
     Nl_, R_, Nfull_ = plan.n_local, plan.R, plan.N

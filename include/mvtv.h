@@ -131,6 +131,10 @@ int mvtv_plan_info(const mvtv_plan *plan, int64_t *N, int64_t *R, int64_t *z0, i
  * exchanges them); a foreign point is MVTV_ERR_INVALID; mean(y) is all-reduced over the ranks. */
 int mvtv_plan_set_points(mvtv_plan *plan, int64_t n, const double *data_colmajor, const double *y,
                          const double *axes);
+/* Same, for a dense data matrix in either layout: element (point i, axis a) = data[i*ld_point + a*ld_axis];
+ * (1, n) is arma::mat's column-major, (p, 1) is a C / numpy row-major n x p array (no host transpose needed). */
+int mvtv_plan_set_points_strided(mvtv_plan *plan, int64_t n, const double *data, int64_t ld_point, int64_t ld_axis,
+                                 const double *y, const double *axes);
 /* Same with inputs already resident in HBM (device pointers on the plan's device). */
 int mvtv_plan_set_points_dev(mvtv_plan *plan, int64_t n, const double *data_colmajor_dev,
                              const double *y_dev, const double *axes_dev);

@@ -27,15 +27,15 @@ __device__ __forceinline__ long long nearest_knot(const double *__restrict__ ax,
 }
 
 // vid[i] = global vertex id of point i; key[i] = local slab vertex (or 0xFFFFFFFF outside the slab)
-__global__ void k_bin(int p, DimTab dt, long long n, const double *__restrict__ data,
-                      const double *__restrict__ axes, long long *__restrict__ vid,
+__global__ void k_bin(int p, DimTab dt, long long n, const double *__restrict__ data, long long ld_point,
+                      long long ld_axis, const double *__restrict__ axes, long long *__restrict__ vid,
                       unsigned *__restrict__ key, unsigned *__restrict__ val) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     long long v = 0, stride = 1, zlast = 0;
     const double *ax = axes;
     for (int a = 0; a < p; ++a) {
-      const long long j = nearest_knot(ax, dt.m[a], data[i + (long long)a * n]);
+      const long long j = nearest_knot(ax, dt.m[a], data[i * ld_point + (long long)a * ld_axis]);
       v += j * stride;
       stride *= dt.m[a];
       ax += dt.m[a];
@@ -90,10 +90,10 @@ static inline int grid_for(long long n, int block = 256) {
   return (int)g;
 }
 
-void launch_bin(int p, const DimTab &dt, long long n, const double *data, const double *axes, long long *vid,
-                unsigned *key, unsigned *val, cudaStream_t st) {
+void launch_bin(int p, const DimTab &dt, long long n, const double *data, long long ld_point, long long ld_axis,
+                const double *axes, long long *vid, unsigned *key, unsigned *val, cudaStream_t st) {
   if (n <= 0) return;
-  k_bin<<<grid_for(n), 256, 0, st>>>(p, dt, n, data, axes, vid, key, val);
+  k_bin<<<grid_for(n), 256, 0, st>>>(p, dt, n, data, ld_point, ld_axis, axes, vid, key, val);
   MVTV_CUDA(cudaGetLastError());
 }
 

@@ -3,8 +3,9 @@
 #include "mvtv_internal.cuh"
 
 namespace mvtv {
-void launch_bin(int p, const DimTab &dt, long long n, const double *data, const double *axes, long long *vid,
-                unsigned *key, unsigned *val, cudaStream_t st);
+// data element of point i, axis a: data[i*ld_point + a*ld_axis]  (column-major: 1, n ; row-major: p, 1)
+void launch_bin(int p, const DimTab &dt, long long n, const double *data, long long ld_point, long long ld_axis,
+                const double *axes, long long *vid, unsigned *key, unsigned *val, cudaStream_t st);
 size_t sort_temp_bytes(long long n);
 void launch_sort(void *temp, size_t temp_bytes, long long n, const unsigned *key_in, unsigned *key_out,
                  const unsigned *val_in, unsigned *val_out, cudaStream_t st);

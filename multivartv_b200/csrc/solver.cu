@@ -469,7 +469,8 @@ struct mvtv_plan {
 
   // ---- points --------------------------------------------------------------------------------
   template <typename T>
-  void set_points_t(long long npts, const double *data_dev, const double *y_dev, const double *axes_dev) {
+  void set_points_t(long long npts, const double *data_dev, long long ld_point, long long ld_axis,
+                    const double *y_dev, const double *axes_dev) {
     use_device();
     MVTV_REQUIRE(npts >= 1 && npts < (1ll << 31), "n must be in [1, 2^31)");
     if (vid) MVTV_CUDA(cudaFree(vid));
@@ -484,7 +485,7 @@ struct mvtv_plan {
     val_out = val_in + npts;
     MVTV_CUDA(cudaMalloc(&temp, std::max<size_t>(tb, 16)));
     try {
-      launch_bin(p, dt, npts, data_dev, axes_dev, vid, key_in, val_in, stream);
+      launch_bin(p, dt, npts, data_dev, ld_point, ld_axis, axes_dev, vid, key_in, val_in, stream);
       launch_sort(temp, tb, npts, key_in, key_out, val_in, val_out, stream);
       const size_t vb = (size_t)dt.usz * esz();
       MVTV_CUDA(cudaMemsetAsync(oty, 0, vb, stream));
@@ -659,7 +660,7 @@ void mvtv_plan::launch_zu(double kappa, double usc, int mode, int init, bool wit
 // tile shapes of k_cg_step per mesh rank (in-plane tile x planes marched by one CTA)
 template <int P> struct StepShape;
 //                                                  Q  TXT XO  TY RY TW DEPTH
-template <> struct StepShape<2> { using Cfg = StepCfg<1, 256, 2,  1, 1, 1, 4>; };   // 512-wide rows, 256 threads, 53 KB
+template <> struct StepShape<2> { using Cfg = StepCfg<1, 256, 2,  1, 1, 1, 3>; };   // 512-wide rows, 256 threads, 41 KB
 template <> struct StepShape<3> { using Cfg = StepCfg<2,  32, 1, 16, 4, 1, 4>; };   // 32x16 tile, 128 threads, 64 KB
 template <> struct StepShape<4> { using Cfg = StepCfg<3,  32, 1,  8, 2, 4, 3>; };   // 32x8x4 tile, 512 threads, 163 KB
 
@@ -1079,16 +1080,23 @@ int mvtv_plan_set_points_dev(mvtv_plan *plan, int64_t n, const double *data_dev,
                              const double *axes_dev) {
   return guarded([&] {
     MVTV_REQUIRE(plan && data_dev && y_dev && axes_dev, "null argument");
-    if (plan->dtype == MVTV_F64) plan->set_points_t<double>(n, data_dev, y_dev, axes_dev);
-    else plan->set_points_t<float>(n, data_dev, y_dev, axes_dev);
+    if (plan->dtype == MVTV_F64) plan->set_points_t<double>(n, data_dev, 1, n, y_dev, axes_dev);
+    else plan->set_points_t<float>(n, data_dev, 1, n, y_dev, axes_dev);
     return MVTV_OK;
   });
 }
 
 int mvtv_plan_set_points(mvtv_plan *plan, int64_t n, const double *data, const double *y, const double *axes) {
+  return mvtv_plan_set_points_strided(plan, n, data, 1, n, y, axes);
+}
+
+int mvtv_plan_set_points_strided(mvtv_plan *plan, int64_t n, const double *data, int64_t ld_point, int64_t ld_axis,
+                                 const double *y, const double *axes) {
   return guarded([&] {
     MVTV_REQUIRE(plan && data && y && axes, "null argument");
     MVTV_REQUIRE(n >= 1, "n must be >= 1");
+    MVTV_REQUIRE((ld_point == 1 && ld_axis == n) || (ld_point == plan->p && ld_axis == 1),
+                 "data must be dense column-major (1, n) or row-major (p, 1)");
     plan->use_device();
     long long na = 0;
     for (int a = 0; a < plan->p; ++a) na += plan->dt.m[a];
@@ -1100,8 +1108,8 @@ int mvtv_plan_set_points(mvtv_plan *plan, int64_t n, const double *data, const d
       MVTV_CUDA(cudaMemcpyAsync(buf, data, sizeof(double) * nd, cudaMemcpyHostToDevice, plan->stream));
       MVTV_CUDA(cudaMemcpyAsync(buf + nd, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, plan->stream));
       MVTV_CUDA(cudaMemcpyAsync(buf + nd + n, axes, sizeof(double) * (size_t)na, cudaMemcpyHostToDevice, plan->stream));
-      if (plan->dtype == MVTV_F64) plan->set_points_t<double>(n, buf, buf + nd, buf + nd + n);
-      else plan->set_points_t<float>(n, buf, buf + nd, buf + nd + n);
+      if (plan->dtype == MVTV_F64) plan->set_points_t<double>(n, buf, ld_point, ld_axis, buf + nd, buf + nd + n);
+      else plan->set_points_t<float>(n, buf, ld_point, ld_axis, buf + nd, buf + nd + n);
     } catch (...) {
       cudaFree(buf);
       throw;
@@ -1285,7 +1293,7 @@ int mvtv_predict(mvtv_plan *plan, int64_t n_new, const double *data, const doubl
     double *d_theta = d_out + n_new;
     MVTV_CUDA(cudaMemcpyAsync(d_data, data, sizeof(double) * nd, cudaMemcpyHostToDevice, s));
     MVTV_CUDA(cudaMemcpyAsync(d_axes, axes, sizeof(double) * (size_t)na, cudaMemcpyHostToDevice, s));
-    launch_bin(plan->p, plan->dt, n_new, d_data, d_axes, d_vid, nullptr, nullptr, s);
+    launch_bin(plan->p, plan->dt, n_new, d_data, 1, n_new, d_axes, d_vid, nullptr, nullptr, s);
     if (theta) {
       MVTV_CUDA(cudaMemcpyAsync(d_theta + plan->dt.plane, theta, sizeof(double) * (size_t)nl, cudaMemcpyHostToDevice, s));
       launch_gather<double>(n_new, d_vid, d_theta, plan->dt.plane, plan->dt.z0, plan->dt.nz, d_out, s);
@@ -1413,7 +1421,7 @@ int mvtv_nearest(int p, const int64_t *m, const double *axes, int64_t n, const d
     if (e == cudaSuccess) e = cudaMemcpy(buf + nd, axes, sizeof(double) * (size_t)na, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
       try {
-        launch_bin(p, dt, n, buf, buf + nd, d_vid, nullptr, nullptr, nullptr);
+        launch_bin(p, dt, n, buf, 1, n, buf + nd, d_vid, nullptr, nullptr, nullptr);
       } catch (...) {
         cudaFree(buf);
         throw;

@@ -70,7 +70,7 @@ struct ZuCfg {
   static constexpr int ST = SX * SY * SW;
   static constexpr int NS = (ST + NT - 1) / NT;
   static constexpr int NF = (1 << Q);           // in-plane offset classes
-  static constexpr int SMEM_ELEMS = 2 * ST + (NF - 1) * 3 * NT;
+  static constexpr int SMEM_ELEMS = 3 * ST + (NF - 1) * 3 * NT;
 };
 
 template <typename T, typename Cfg, int V>
@@ -82,8 +82,8 @@ k_zu_march(const __grid_constant__ DimTab dt, const __grid_constant__ BlockTab b
   constexpr int NF = Cfg::NF, K = zu_num_blocks(P, V);
   constexpr int ZBIT = 1 << Q;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *sth = reinterpret_cast<T *>(smem_raw);  // [2][ST] theta planes zz (slot zz&1) and zz+1
-  T *sh = sth + 2 * ST;                      // [(NF-1)][3][NT] in-plane exchange
+  T *sth = reinterpret_cast<T *>(smem_raw);  // [3][ST] theta planes zz, zz+1 and (in flight) zz+2; slot = plane % 3
+  T *sh = sth + 3 * ST;                      // [(NF-1)][3][NT] in-plane exchange
 
   const int tid = threadIdx.x;
   const int m0 = (int)dt.m[0];
@@ -134,15 +134,16 @@ k_zu_march(const __grid_constant__ DimTab dt, const __grid_constant__ BlockTab b
   const int zhi = dt.has_hi ? dt.nz : dt.nz - 1;
   const T kappa = (T)a.kappa, usc = (T)a.uscale;
 
-  auto load_theta = [&](int z) {  // plane clamp(z) -> slot (z & 1)
+  auto load_theta = [&](int z) {  // cp.async: plane clamp(z) -> slot (z+3) % 3; always commits a group
     const int zs = min(max(z, zlo), zhi);
     const long long pb = (long long)(zs + 1) * dt.plane;
-    T *dst = sth + ((z + 2) & 1) * ST;
+    T *dst = sth + ((z + 3) % 3) * ST;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
       const int e = tid + k * NT;
-      if (e < ST) dst[e] = a.theta[pb + tsrc[k]];
+      if (e < ST) cp_async<sizeof(T)>(dst + e, a.theta + pb + tsrc[k]);
     }
+    cp_async_commit();
   };
   // u_old of this thread's rows in plane z (prefetched one plane ahead)
   auto load_u = [&](int z, T (&dst)[K]) {
@@ -162,16 +163,23 @@ k_zu_march(const __grid_constant__ DimTab dt, const __grid_constant__ BlockTab b
   // first plane processed: zc0-1 (pre-step, only to build the carry) unless it lies below the global mesh
   const int zstart = (dt.z0 + zc0 - 1 >= 0) ? zc0 - 1 : zc0;
   T ucur[K], unext[K];
+  T thp_cur = T(0), thp_next = T(0);                  // theta_old of this vertex, prefetched like u
   load_theta(zstart);
+  load_theta(zstart + 1);
   load_u(zstart, ucur);
+  if (a.theta_prev && owned_xy && zstart >= zc0) thp_cur = a.theta_prev[(long long)(zstart + 1) * dt.plane + qoff];
   for (int zz = zstart; zz < zc1; ++zz) {
     const bool pre = zz < zc0;                        // pre-step: rows are owned by the previous chunk / rank
     const bool ghostrow = pre && zz < 0;              // ... except the ghost plane's rows, kept up to date here
-    load_theta(zz + 1);
-    if (zz + 1 < zc1) load_u(zz + 1, unext);
-    __syncthreads();  // theta planes zz, zz+1 visible; previous plane's exchange buffer fully consumed
-    const T *t0 = sth + ((zz + 2) & 1) * ST;
-    const T *t1 = sth + ((zz + 3) & 1) * ST;
+    load_theta(zz + 2);
+    if (zz + 1 < zc1) {
+      load_u(zz + 1, unext);
+      if (a.theta_prev && owned_xy) thp_next = a.theta_prev[(long long)(zz + 2) * dt.plane + qoff];
+    }
+    cp_async_wait<1>();  // this thread's copies of planes <= zz+1 have landed
+    __syncthreads();     // ... everybody's; previous plane's exchange buffer fully consumed
+    const T *t0 = sth + ((zz + 3) % 3) * ST;
+    const T *t1 = sth + ((zz + 4) % 3) * ST;
     const long long gz = dt.z0 + zz;
     const bool z_hi_ok = gz + 1 < mz;
     const long long pb = (long long)(zz + 1) * dt.plane + qoff;
@@ -256,7 +264,7 @@ k_zu_march(const __grid_constant__ DimTab dt, const __grid_constant__ BlockTab b
         const double sv = (a.mode == MVTV_MODE_RCPP) ? (double)t2s - (double)t3s : (double)t1s + (double)t3s;
         red[ZR_S2] += sv * sv;
         red[ZR_DTU2] += (double)t2s * (double)t2s;
-        if (a.theta_prev) red[ZR_DMAX] = fmax(red[ZR_DMAX], fabs((double)th_c - (double)a.theta_prev[pb]));
+        if (a.theta_prev) red[ZR_DMAX] = fmax(red[ZR_DMAX], fabs((double)th_c - (double)thp_cur));
       }
     } else {
       __syncthreads();  // nobody may refill a theta slot while the pre-step's rows are still being evaluated
@@ -269,7 +277,9 @@ k_zu_march(const __grid_constant__ DimTab dt, const __grid_constant__ BlockTab b
       constexpr int b = decltype(bc)::value;
       ucur[b] = unext[b];
     });
+    thp_cur = thp_next;
   }
+  cp_async_wait<0>();
   double *out = a.red_out;
   grid_reduce<ZR_N, ZR_NSUM>(red, rb, [out](const double (&res)[ZR_N]) {
 #pragma unroll

@@ -192,14 +192,23 @@ class Plan:
 
     # -- points (A = O) ----------------------------------------------------------------------
     def set_points(self, data, y, axes):
-        dcm, n, p = _colmajor(data)
+        data = np.asarray(data, dtype=np.float64)
+        if data.ndim == 1:
+            data = data[:, None]
+        n, p = data.shape
         assert p == self.p, "data has %d columns, mesh has %d axes" % (p, self.p)
+        # pass the matrix in the layout it already has (no host transpose): F-order = arma's column-major
+        if data.flags.f_contiguous:
+            ld_point, ld_axis = 1, n
+        else:
+            data = np.ascontiguousarray(data)
+            ld_point, ld_axis = p, 1
         y = _f64(np.asarray(y).ravel())
         assert y.size == n
         self.axes = [np.asarray(a, dtype=np.float64) for a in axes]
         ax = _f64(np.concatenate(self.axes))
         assert ax.size == sum(self.m)
-        _lib.check(_lib.load().mvtv_plan_set_points(self._h, n, _dp(dcm), _dp(y), _dp(ax)))
+        _lib.check(_lib.load().mvtv_plan_set_points_strided(self._h, n, _dp(data), ld_point, ld_axis, _dp(y), _dp(ax)))
         self.n = n
         return self
 
