@@ -165,14 +165,21 @@ int mvtv_solve(mvtv_plan *plan, const mvtv_solve_params *prm, const double *thet
  * order, each warm-started from the previous one WITHOUT leaving the device (CPP/PY mode: theta carried, system
  * matrix crossO + lambda_i*crossD; RCPP mode: theta, u and rho carried, first-pass matrix crossO + rho*crossD).
  * prm->lambda is ignored.  ftrue: n doubles (pass y for the reference default, gen_ftrue solvers.cpp:235-244).
- * mses_out[i] = mse(fitted_i, ftrue) (n_lambda doubles); counters_out (nullable); thetas_out (nullable,
- * n_lambda x N); theta_best_out / fitted_best_out / best_index_out: the first lambda attaining the lowest MSE
+ * mses_out[i] = mse(fitted_i, ftrue) (n_lambda doubles); counters_out, rhos_out (final rho of each solve) and
+ * thetas_out (n_lambda x N) are nullable; theta_best_out / fitted_best_out / best_index_out: the first lambda attaining the lowest MSE
  * (fill_output_mbs, solvers.cpp:170-177).  total: passes, inner iterations, device seconds summed over the path.
  * A CPP-mode non-convergence stops the path with MVTV_ERR_NOT_CONVERGED, like the uncaught throw upstream. */
 int mvtv_solve_path(mvtv_plan *plan, const mvtv_solve_params *prm, int32_t n_lambda, const double *lambdas,
-                    const double *ftrue, double *mses_out, int32_t *counters_out, double *thetas_out,
-                    double *theta_best_out, double *fitted_best_out, int32_t *best_index_out,
+                    const double *ftrue, double *mses_out, int32_t *counters_out, double *rhos_out,
+                    double *thetas_out, double *theta_best_out, double *fitted_best_out, int32_t *best_index_out,
                     mvtv_solve_result *total);
+
+/* Replaces: lam_max_pinv / mypinv / cg (cpp-code/utils.cpp:354-404 for MVTV_MODE_CPP and _PY: CG on D^T D from
+ * x0 = mean(Oty), stop at ||r|| < 0.01 or 100 (500 if N < 400) iterations, lambda_max = max|D x|;
+ * rcpp-code/MultivarTV/src/utils.cpp:306-355 for MVTV_MODE_RCPP: CGNR, relative 1e-4, min(N,2000) iterations,
+ * 5*||D x||_inf).  The CG is truncated, not converged, so the value is only reproducible to ~1e-6 relative across
+ * arithmetic orders.  The lambda grid itself (create_lambdas, cpp solvers.cpp:179-192) is host arithmetic. */
+int mvtv_lambda_max(mvtv_plan *plan, int mode, double *lambda_max, int32_t *cg_iters);
 
 /* Replaces: mbs_predict (cpp-code/solvers.hpp:93): nearest vertex of each new point, gather theta. */
 int mvtv_predict(mvtv_plan *plan, int64_t n_new, const double *data_colmajor, const double *axes,

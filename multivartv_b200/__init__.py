@@ -7,8 +7,9 @@ Importing the package does not load the library; the first call does, and fails 
 from . import _lib  # noqa: F401
 from ._lib import (F32, F64, MODE_CPP, MODE_PY, MODE_RCPP, PRECOND_JACOBI, VARIANT_INTENDED,  # noqa: F401
                    VARIANT_REFERENCE, WARM_THETA_FROM_PLAN, WARM_U_FROM_PLAN, MvtvError, NotConverged)
-from .solvers import (Plan, axes_from_mesh, create_deltas, create_mesh, mbs_mse, mbs_one, mbs_predict,  # noqa: F401
+from .solvers import (Plan, axes_from_mesh, create_deltas, create_lambdas, create_mesh, kfoldinds, mbs, mbs_mse,  # noqa: F401
+                      mbs_one, mbs_predict,
                       mesh_axes, mesh_from_axes, nccl_unique_id, nearest1, softthresh)
 
-__all__ = ["Plan", "mbs_one", "mbs_predict", "mbs_mse", "softthresh", "nearest1", "create_mesh", "mesh_axes",
+__all__ = ["Plan", "mbs", "create_lambdas", "kfoldinds", "mbs_one", "mbs_predict", "mbs_mse", "softthresh", "nearest1", "create_mesh", "mesh_axes",
            "mesh_from_axes", "axes_from_mesh", "create_deltas", "MvtvError", "NotConverged"]

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmvtv_b200.so")
 
 SYMBOLS = [
     "mvtv_abi_version", "mvtv_last_error", "mvtv_device_count", "mvtv_nccl_unique_id", "mvtv_plan_create", "mvtv_plan_destroy",
-    "mvtv_plan_info", "mvtv_plan_profile", "mvtv_plan_get_profile", "mvtv_plan_set_points", "mvtv_plan_set_points_strided", "mvtv_plan_set_points_dev", "mvtv_plan_get_cache", "mvtv_solve", "mvtv_solve_path",
+    "mvtv_plan_info", "mvtv_plan_profile", "mvtv_plan_get_profile", "mvtv_plan_set_points", "mvtv_plan_set_points_strided", "mvtv_plan_set_points_dev", "mvtv_plan_get_cache", "mvtv_solve", "mvtv_solve_path", "mvtv_lambda_max",
     "mvtv_predict", "mvtv_apply_D", "mvtv_apply_Dt", "mvtv_apply_M", "mvtv_softthresh", "mvtv_nearest",
 ]
 
@@ -87,8 +87,9 @@ def load():
     L.mvtv_plan_set_points_dev.argtypes = [vp, C.c_int64, vp, vp, vp]
     L.mvtv_plan_get_cache.argtypes = [vp, dp, dp, ip]
     L.mvtv_solve.argtypes = [vp, C.POINTER(SolveParams), dp, dp, dp, dp, C.POINTER(SolveResult)]
-    L.mvtv_solve_path.argtypes = [vp, C.POINTER(SolveParams), C.c_int32, dp, dp, dp, C.POINTER(C.c_int32), dp, dp, dp,
+    L.mvtv_solve_path.argtypes = [vp, C.POINTER(SolveParams), C.c_int32, dp, dp, dp, C.POINTER(C.c_int32), dp, dp, dp, dp,
                                   C.POINTER(C.c_int32), C.POINTER(SolveResult)]
+    L.mvtv_lambda_max.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int32)]
     L.mvtv_predict.argtypes = [vp, C.c_int64, dp, dp, dp, dp]
     L.mvtv_apply_D.argtypes = [vp, dp, dp]
     L.mvtv_apply_Dt.argtypes = [vp, dp, dp]

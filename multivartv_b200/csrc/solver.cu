@@ -528,6 +528,8 @@ struct mvtv_plan {
   template <typename T>
   int solve_t(const mvtv_solve_params &prm, const double *theta_init, double *u_inout, double *theta_out,
               double *fitted_out, mvtv_solve_result &res);
+  template <typename T, int P>
+  int lambda_max_t(int mode, double *lam_out, int *iters_out);
   template <typename T>
   void read_scalars(const double *dev, int count) {
     MVTV_CUDA(cudaMemcpyAsync(h_scal, dev, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
@@ -564,6 +566,47 @@ __global__ void __launch_bounds__(256) k_sqerr(const long long *__restrict__ vid
     red[0] += d * d;
   }
   grid_reduce<1, 1>(red, rb, [out](const double (&res)[1]) { out[0] = res[0]; });
+}
+
+
+// ---- small generic kernels for the one-off lambda_max estimate (cpp-code/utils.cpp:354-404) -------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_axpby(T *out, double a, const T *x, double b, const T *y, long long plane,
+                                               long long nloc) {  // out = a*x + b*y on the owned slab
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (long long)gridDim.x * blockDim.x)
+    out[plane + i] = (T)(a * (double)x[plane + i] + b * (double)y[plane + i]);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_dot(const T *x, const T *y, long long plane, long long nloc, RedBuf rb,
+                                             double *out) {
+  double red[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (long long)gridDim.x * blockDim.x)
+    red[0] += (double)x[plane + i] * (double)y[plane + i];
+  grid_reduce<1, 1>(red, rb, [out](const double (&res)[1]) { out[0] = res[0]; });
+}
+// max over the rows of D of |(D x)_row|   (lam_max_pinv: max(abs(a*b)), cpp-code/utils.cpp:399-404)
+template <typename T>
+__global__ void __launch_bounds__(256) k_maxabs_D(const __grid_constant__ DimTab dt, const __grid_constant__ BlockTab bt,
+                                                  const T *x, RedBuf rb, double *out) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int zl = blockIdx.y;
+  double red[1] = {0.0};
+  if (q < dt.plane) {
+    int lo_ok, hi_ok;
+    boundary_masks(dt, q, zl, lo_ok, hi_ok);
+    const long long base = (long long)(zl + 1) * dt.plane + q;
+    for (int b = 0; b < bt.K; ++b) {
+      const int S = bt.mask[b];
+      if ((S & ~hi_ok) != 0) continue;
+      double d = 0.0;
+      for (int f = 0; f < bt.nsub[b]; ++f) {
+        const double t = (double)x[base + bt.off[b][f]];
+        d += (__popc(bt.sub[b][f]) & 1) ? -t : t;
+      }
+      red[0] = fmax(red[0], fabs(bt.scale[b] * d));
+    }
+  }
+  grid_reduce<1, 0>(red, rb, [out](const double (&res)[1]) { out[0] = res[0]; });
 }
 
 void mvtv_plan::sum_y(const double *y_dev, long long npts) {
@@ -794,6 +837,98 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   inner += (long long)iters;
   last_cg_iters = (int)iters + 1;
   return (int)iters;
+}
+
+
+// lam_max_pinv: a truncated CG on D^T D started from Oty, then max|D x| (cpp-code/utils.cpp:354-404), or the CGNR
+// variant times five (rcpp-code/MultivarTV/src/utils.cpp:306-355).  One-off setup: host-driven loop, generic kernels.
+template <typename T, int P>
+int mvtv_plan::lambda_max_t(int mode, double *lam_out, int *iters_out) {
+  use_device();
+  MVTV_REQUIRE(have_points, "mvtv_lambda_max: call mvtv_plan_set_points first");
+  const long long pl = dt.plane, nl = dt.Nloc;
+  const size_t vb = (size_t)dt.usz * esz();
+  T *X = (T *)xold, *R = (T *)r, *Pv = (T *)pbuf[0], *AP = (T *)q, *Z0 = (T *)pbuf[1], *Dv = (T *)v1, *B = (T *)oty;
+  const dim3 g = grid_owned();
+  const int g1 = std::min<int>(grid1d(nl), (int)nblocks);
+  MVTV_CUDA(cudaMemsetAsync(Z0, 0, vb, stream));
+  auto applyK = [&](T *in, T *out) {  // out = D^T D in  (3^P-point clamped stencil, diag(c) = 0)
+    exchange_ghosts<T>(in);
+    k_apply_M<T, P><<<g, block, 0, stream>>>(dt, st, in, Z0, 1.0, out);
+    launches += 1;
+  };
+  auto dot = [&](const T *a_, const T *b_) {
+    k_dot<T><<<g1, 256, 0, stream>>>(a_, b_, pl, nl, RedBuf{partials, counters + 4}, zr);
+    launches += 1;
+    allreduce(zr, 1, ncclSum);
+    read_scalars<T>(zr, 1);
+    return h_scal[0];
+  };
+  auto axpby = [&](T *out, double a_, const T *x_, double b_, const T *y_) {
+    k_axpby<T><<<g1, 256, 0, stream>>>(out, a_, x_, b_, y_, pl, nl);
+    launches += 1;
+  };
+  int iter = 0;
+  if (mode == MVTV_MODE_CPP || mode == MVTV_MODE_PY) {
+    // x.fill(mean(b)); r = b - A*x; p = r     (utils.cpp:356-358)
+    double sumb;
+    {
+      // mean(b) over ALL vertices
+      MVTV_CUDA(cudaMemsetAsync(AP, 0, vb, stream));
+      k_fill<T><<<grid1d(dt.usz), 256, 0, stream>>>(AP, dt.usz, (T)1.0);
+      sumb = dot(B, AP);
+    }
+    const double meanb = sumb / (double)N;
+    k_fill<T><<<grid1d(dt.usz), 256, 0, stream>>>(X, dt.usz, (T)meanb);
+    applyK(X, AP);
+    axpby(R, 1.0, B, -1.0, AP);
+    axpby(Pv, 1.0, R, 0.0, R);
+    double rsold = dot(R, R), rsnew = rsold + 1.0;
+    const int MAXIT = (N < 400) ? 500 : 100;                  // utils.cpp:364-370
+    while (sqrt(rsnew) >= 0.01) {                             // utils.cpp:371
+      applyK(Pv, AP);
+      const double alpha = rsold / dot(Pv, AP);
+      axpby(X, 1.0, X, alpha, Pv);
+      axpby(R, 1.0, R, -alpha, AP);
+      rsnew = dot(R, R);
+      iter += 1;
+      if (iter == MAXIT) break;                               // "Reached max iter!" utils.cpp:378-381
+      axpby(Pv, 1.0, R, rsnew / rsold, Pv);
+      rsold = rsnew;
+    }
+  } else {
+    // rcpp CGNR on A = D^T D (rcpp utils.cpp:306-340): x = 0; d = b; r = A^T d; p = r; t = A p
+    MVTV_CUDA(cudaMemsetAsync(X, 0, vb, stream));
+    axpby(Dv, 1.0, B, 0.0, B);
+    applyK(Dv, R);
+    axpby(Pv, 1.0, R, 0.0, R);
+    const double rsold0 = sqrt(dot(R, R));
+    double rsold = rsold0 * rsold0, rsnew = rsold + 1.0;
+    applyK(Pv, AP);
+    const int MAXIT = N < 2000 ? (int)N : 2000;
+    while (sqrt(rsnew) >= 0.0001 * rsold0) {
+      const double alpha = rsold / dot(AP, AP);
+      axpby(X, 1.0, X, alpha, Pv);
+      axpby(Dv, 1.0, Dv, -alpha, AP);
+      applyK(Dv, R);
+      rsnew = dot(R, R);
+      iter += 1;
+      if (iter == MAXIT) break;
+      axpby(Pv, 1.0, R, rsnew / rsold, Pv);
+      applyK(Pv, AP);
+      rsold = rsnew;
+    }
+  }
+  exchange_ghosts<T>(X);
+  k_maxabs_D<T><<<g, block, 0, stream>>>(dt, bt, X, RedBuf{partials, counters + 4}, zr);
+  launches += 1;
+  allreduce(zr, 1, ncclMax);
+  read_scalars<T>(zr, 1);
+  MVTV_CUDA(cudaGetLastError());
+  *lam_out = (mode == MVTV_MODE_RCPP) ? 5.0 * h_scal[0] : h_scal[0];   // rcpp utils.cpp:351-355
+  if (iters_out) *iters_out = iter;
+  dinv_rho = NAN;  // scratch vectors were borrowed from the CG loop
+  return MVTV_OK;
 }
 
 template <typename T>
@@ -1161,7 +1296,7 @@ int mvtv_solve(mvtv_plan *plan, const mvtv_solve_params *prm, const double *thet
 }
 
 int mvtv_solve_path(mvtv_plan *plan, const mvtv_solve_params *prm, int32_t n_lambda, const double *lambdas,
-                    const double *ftrue, double *mses_out, int32_t *counters_out, double *thetas_out,
+                    const double *ftrue, double *mses_out, int32_t *counters_out, double *rhos_out, double *thetas_out,
                     double *theta_best_out, double *fitted_best_out, int32_t *best_index_out, mvtv_solve_result *total) {
   return guarded([&] {
     MVTV_REQUIRE(plan && prm && lambdas && ftrue && mses_out && total, "null argument");
@@ -1230,6 +1365,7 @@ int mvtv_solve_path(mvtv_plan *plan, const mvtv_solve_params *prm, int32_t n_lam
         const double m = plan->h_scal[0] / cnt;
         mses_out[i] = m;
         if (counters_out) counters_out[i] = r.counter;
+        if (rhos_out) rhos_out[i] = r.rho;
         if (m < best_mse) {  // first instance of the lowest MSE (cpp solvers.cpp:172-175)
           best_mse = m;
           best = i;
@@ -1269,6 +1405,25 @@ int mvtv_solve_path(mvtv_plan *plan, const mvtv_solve_params *prm, int32_t n_lam
       throw;
     }
     MVTV_CUDA(cudaFree(d_target));
+    return rc;
+  });
+}
+
+int mvtv_lambda_max(mvtv_plan *plan, int mode, double *lambda_max, int32_t *cg_iters) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && lambda_max, "null argument");
+    int it = 0;
+    int rc;
+#define MVTV_LM(TT)                                                          \
+  switch (plan->dt.P) {                                                      \
+    case 2: rc = plan->lambda_max_t<TT, 2>(mode, lambda_max, &it); break;    \
+    case 3: rc = plan->lambda_max_t<TT, 3>(mode, lambda_max, &it); break;    \
+    case 4: rc = plan->lambda_max_t<TT, 4>(mode, lambda_max, &it); break;    \
+    default: throw Error(MVTV_ERR_UNSUPPORTED, "p must be 1..4");            \
+  }
+    if (plan->dtype == MVTV_F64) { MVTV_LM(double) } else { MVTV_LM(float) }
+#undef MVTV_LM
+    if (cg_iters) *cg_iters = it;
     return rc;
   });
 }

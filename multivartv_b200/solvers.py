@@ -286,19 +286,27 @@ class Plan:
         nl = lambdas.size
         mses = np.empty(nl)
         counters = np.zeros(nl, dtype=np.int32)
+        rhos = np.zeros(nl)
         thetas = np.empty((nl, self.n_local)) if want_thetas else None
         tb = np.empty(self.n_local) if want_best else None
         fb = np.empty(self.n) if want_best else None
         best = C.c_int32(0)
         res = _lib.SolveResult()
         code = L.mvtv_solve_path(self._h, C.byref(prm), nl, _dp(lambdas), _dp(ftrue), _dp(mses),
-                                 counters.ctypes.data_as(C.POINTER(C.c_int32)), _dp(thetas), _dp(tb), _dp(fb),
+                                 counters.ctypes.data_as(C.POINTER(C.c_int32)), _dp(rhos), _dp(thetas), _dp(tb), _dp(fb),
                                  C.byref(best), C.byref(res))
         _lib.check(code)
-        return dict(mses=mses, counters=counters, thetas=thetas, theta_best=tb, fitted_best=fb, best_index=best.value,
+        return dict(mses=mses, counters=counters, rhos=rhos, thetas=thetas, theta_best=tb, fitted_best=fb, best_index=best.value,
                     minmse=float(mses[best.value]), minmse_lambda=float(lambdas[best.value]), passes=res.passes,
                     inner_iters=int(res.inner_iters), device_seconds=res.device_seconds, rho=res.rho,
                     kernel_launches=int(res.kernel_launches), status=res.status)
+
+    def lambda_max(self, mode="cpp"):
+        """lam_max_pinv (cpp-code/utils.cpp:399-404 ; rcpp utils.cpp:351-355): returns (lambda_max, cg_iterations)."""
+        lam = C.c_double(0.0)
+        it = C.c_int32(0)
+        _lib.check(_lib.load().mvtv_lambda_max(self._h, _MODES[mode], C.byref(lam), C.byref(it)))
+        return lam.value, it.value
 
     def predict(self, data, theta=None, axes=None):
         """mbs_predict (cpp-code/solvers.cpp:154-158)."""
@@ -397,3 +405,95 @@ def mbs_mse(mbs_one_object, y):
     yhat = np.asarray(mbs_one_object["fitted"]).ravel()
     ytrue = np.asarray(y).ravel()
     return float(np.sum((yhat - ytrue) ** 2) / ytrue.size)
+
+
+# ----------------------------------------------------------------------------------------------
+# model-selection driver (host orchestration of the device path)
+# ----------------------------------------------------------------------------------------------
+def create_lambdas(n_lambda, lambda_max, mode="cpp"):
+    """cpp-code/solvers.cpp:185 (1e-5*lambda_max .. lambda_max) ; rcpp solvers.cpp:191 (1e-4*lambda_max ..)."""
+    lo = 0.00001 if _MODES[mode] == MODE_CPP else 0.0001
+    return np.flipud(np.exp(_arma_linspace(math.log(lambda_max * lo), math.log(lambda_max), n_lambda)))
+
+
+def kfoldinds(n, k, seed=117):
+    """rcpp utils.cpp:367-376: indices i % k, shuffled (our own seeded shuffle: arma's RNG stream is not reproducible)."""
+    idx = np.arange(n) % k
+    np.random.RandomState(seed).shuffle(idx)
+    return idx
+
+
+def mbs(data, y, m, mesh=None, n_lambda=100, ftrue=None, lambdas=None, folds=5, verbose=False, mode="rcpp",
+        foldinds=None, seed=117, dtype=F64, variant=VARIANT_REFERENCE, **solve_kw):
+    """Cross-validated fit over a path of lambdas: ``mbs`` / ``mbs_impl`` (cpp-code/solvers.cpp:277-310,
+    rcpp-code/MultivarTV/src/solvers.cpp:305-376).  Follows the rcpp semantics (per-fold operators, fresh path per
+    fold; SURVEY section 3 lists the cpp-code CV bugs).  ``mode`` selects the ADMM loop ("cpp" / "rcpp").
+    Returns the rcpp list as a dict plus the Python prototype's keys (code/solvers.py:140)."""
+    data = np.asarray(data, dtype=np.float64)
+    if data.ndim == 1:
+        data = data[:, None]
+    y = np.asarray(y, dtype=np.float64).ravel()
+    m = [int(v) for v in np.asarray(m).ravel()]
+    n = y.size
+    deltas = create_deltas(data, m, mode)                      # inits.deltas (cpp :281 / rcpp :310)
+    axes = mesh_axes(data, m, mode) if mesh is None else (
+        [np.asarray(a, dtype=np.float64) for a in mesh] if isinstance(mesh, (list, tuple)) else axes_from_mesh(mesh, m))
+    FTRUE = y if ftrue is None else np.asarray(ftrue, dtype=np.float64).ravel()
+    plan = Plan(m, deltas=deltas, dtype=dtype, variant=variant)
+    try:
+        plan.set_points(data, y, axes)                         # create_cache_objects on the full data
+        if lambdas is None:
+            lam_max, _ = plan.lambda_max(mode)
+            if verbose:
+                print("lambda_max = %f" % lam_max)
+            LAMBDAS = create_lambdas(n_lambda, lam_max, mode)
+        else:
+            LAMBDAS = np.asarray(lambdas, dtype=np.float64).ravel()
+        nl = LAMBDAS.size
+        mse_mat = np.zeros((nl, max(1, folds)))
+        if folds <= 1:
+            final = plan.solve_path(LAMBDAS, FTRUE, mode=mode, want_thetas=True, **solve_kw)
+            idx_all = plan.cache()[2]
+            for i in range(nl):                                 # test_mse on the training data itself (rcpp :330)
+                mse_mat[i, 0] = mbs_mse({"fitted": final["thetas"][i][idx_all]}, y)
+            mean_mses = mse_mat[:, 0].copy()
+            best1 = int(np.argmin(mean_mses))
+            # mbs_fit_optimal: refit at the best lambda; the cached system matrix is whatever mbs_path left behind
+            if _MODES[mode] == MODE_RCPP:   # rcpp solvers.cpp:261-274: cold start, rho = lambdas[0]/5, stale matrix scalar
+                stale = final["rhos"][nl - 2] if nl >= 2 else LAMBDAS[0] / 5.0
+                refit = plan.solve(LAMBDAS[best1], mode=mode, rho_init=LAMBDAS[0] / 5.0, rho_matrix0=stale, **solve_kw)
+            else:                           # cpp solvers.cpp:248-260: warm start from the path's theta, matrix of the last lambda
+                refit = plan.solve(LAMBDAS[best1], mode=mode, theta_init=final["thetas"][best1],
+                                   rho_matrix0=LAMBDAS[-1], **solve_kw)
+        else:
+            if foldinds is None:
+                foldinds = kfoldinds(n, folds, seed)
+            foldinds = np.asarray(foldinds)
+            for f in range(folds):
+                tr, te = foldinds != f, foldinds == f
+                plan.set_points(data[tr], y[tr], axes)          # per-fold operators (rcpp :347-348)
+                path = plan.solve_path(LAMBDAS, y[tr], mode=mode, want_thetas=True, want_best=False, **solve_kw)
+                idx_te = nearest1(data[te], axes=axes)
+                for i in range(nl):                             # test_mse (rcpp :278-288)
+                    mse_mat[i, f] = float(np.sum((path["thetas"][i][idx_te] - y[te]) ** 2) / te.sum())
+                if verbose:
+                    print("Fold Complete: %d" % f)
+            plan.set_points(data, y, axes)                      # final path on the full data (rcpp :355-358)
+            final = plan.solve_path(LAMBDAS, y, mode=mode, want_thetas=True, **solve_kw)
+            idx_all = plan.cache()[2]
+            mean_mses = mse_mat.mean(axis=1)                    # rowmean (rcpp :359)
+        best = int(np.argmin(mean_mses))                        # index_min: first minimum
+        theta_hat = refit["theta"] if folds <= 1 else final["thetas"][best]
+        fitted = theta_hat[idx_all]
+        models = [{"lambda": float(LAMBDAS[i]), "mse": float(final["mses"][i]), "theta_hat": final["thetas"][i],
+                   "fitted": final["thetas"][i][idx_all]} for i in range(nl)]
+    finally:
+        plan.close()
+    out = {"data": data, "fitted": fitted, "m": m, "mesh": mesh_from_axes(axes), "theta_hat": theta_hat, "y": y,
+           "residuals": y - fitted, "models": models, "lambda_minmse_ind": best + 1, "cv.mses": mean_mses,
+           "lambdas": LAMBDAS, "cv.mse_mat": mse_mat, "axes": axes, "counters": final["counters"]}
+    out["minmse.fits"] = {"mesh": out["mesh"], "theta.hat": theta_hat, "fitted": fitted, "data": data, "y": y, "m": m,
+                          "axes": axes}
+    out["minmse"] = float(mean_mses[best])
+    out["minmse.lam"] = float(LAMBDAS[best])
+    return out

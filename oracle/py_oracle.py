@@ -540,3 +540,74 @@ def mse(fits, y):
     """cpp-code/solvers.cpp:160-163."""
     fits, y = np.asarray(fits).ravel(), np.asarray(y).ravel()
     return float(np.sum((fits - y) ** 2) / y.size)
+
+
+# --------------------------------------------------------------------------------------
+# lambda_max and the lambda grid -- cpp-code/utils.cpp:354-404, solvers.cpp:179-192 ; rcpp utils.cpp:306-355
+# --------------------------------------------------------------------------------------
+def cg_cpp(A, b):
+    """cpp-code/utils.cpp:354-386 -- truncated CG from x0 = mean(b), abs tol 0.01, MAXIT 100 (500 if n < 400)."""
+    b = np.asarray(b, dtype=np.float64)
+    x = np.full(b.shape[0], float(np.mean(b)))
+    r = b - A @ x
+    p = r.copy()
+    rsold = float(r @ r)
+    rsnew = rsold + 1.0
+    it = 0
+    MAXIT = 500 if b.shape[0] < 400 else 100
+    while math.sqrt(rsnew) >= 0.01:
+        Ap = A @ p
+        alpha = rsold / float(p @ Ap)
+        x = x + alpha * p
+        r = r - alpha * Ap
+        rsnew = float(r @ r)
+        it += 1
+        if it == MAXIT:
+            break
+        p = r + (rsnew / rsold) * p
+        rsold = rsnew
+    return x, it
+
+
+def cg_rcpp(A, b):
+    """rcpp-code/MultivarTV/src/utils.cpp:306-340 -- CGNR, relative tolerance 1e-4, MAXIT min(n, 2000)."""
+    b = np.asarray(b, dtype=np.float64)
+    x = np.zeros(b.shape[0])
+    d = b - A @ x
+    r = A.T @ d
+    p = r.copy()
+    rsold0 = float(np.linalg.norm(r))
+    rsold = rsold0 ** 2
+    rsnew = rsold + 1.0
+    t = A @ p
+    it = 0
+    MAXIT = b.shape[0] if b.shape[0] < 2000 else 2000
+    while math.sqrt(rsnew) >= 0.0001 * rsold0:
+        alpha = rsold / float(np.linalg.norm(t)) ** 2
+        x = x + alpha * p
+        d = d - alpha * t
+        r = A.T @ d
+        rsnew = float(np.linalg.norm(r)) ** 2
+        it += 1
+        if it == MAXIT:
+            break
+        p = r + (rsnew / rsold) * p
+        t = A @ p
+        rsold = rsnew
+    return x, it
+
+
+def lam_max_pinv(D, Oty, mode=MODE_CPP):
+    """cpp-code/utils.cpp:389-404 (max|D b|) ; rcpp utils.cpp:343-355 (5 * ||D b||_inf)."""
+    ata = (D.T @ D).tocsr()
+    if mode == MODE_RCPP:
+        b, it = cg_rcpp(ata, Oty)
+        return 5.0 * float(np.max(np.abs(D @ b))), it
+    b, it = cg_cpp(ata, Oty)
+    return float(np.max(np.abs(D @ b))), it
+
+
+def create_lambdas(n_lambda, lambda_max, mode=MODE_CPP):
+    """cpp-code/solvers.cpp:185 ; rcpp solvers.cpp:191."""
+    lo = 0.00001 if mode == MODE_CPP else 0.0001
+    return np.flipud(np.exp(arma_linspace(math.log(lambda_max * lo), math.log(lambda_max), n_lambda)))
