@@ -116,6 +116,10 @@ def stage_bytes(N, R, esz):
         "cg_init": esz * (8 * N),         # read theta, c, dinv, Oty, v1, v2 ; write r, theta_old
         "cg_step": esz * (6 * N),         # read r, dinv, p_old, c ; write p_new, q
         "cg_update": esz * (7 * N),       # read theta, p, r, q, dinv ; write theta, r
+        # MVTV_PRECOND_CHEB1 variants
+        "cg_prec": esz * (4 * N),         # read r, dinv, c ; write z
+        "cg_step_z": esz * (5 * N),       # read z, p_old, c ; write p_new, q
+        "cg_update_p": esz * (6 * N),     # read theta, p, r, q ; write theta, r
     }
 
 
@@ -219,7 +223,9 @@ def run_ours(args):
     # ---- warm-up: operators + W passes ------------------------------------------------------------
     plan.set_points(x, y, axes)
     mode = args.mode
-    kw = dict(mode=mode, cg_rtol=args.cg_rtol, want_theta=False, want_fitted=False, raise_on_nonconvergence=False)
+    precond = {"cheb1": mv.PRECOND_CHEB1, "jacobi": mv.PRECOND_JACOBI}[args.precond]
+    kw = dict(mode=mode, cg_rtol=args.cg_rtol, want_theta=False, want_fitted=False, raise_on_nonconvergence=False,
+              precond=precond)
     rw = plan.solve(args.lam, max_passes=max(1, args.warmup), **kw)
     warm = mv.WARM_THETA_FROM_PLAN | mv.WARM_U_FROM_PLAN
 
@@ -257,7 +263,7 @@ def run_ours(args):
         plan.set_points(x, y, axes)
         t_sp = time.perf_counter() - t0
         re = plan.solve(args.lam, max_passes=args.steps, mode=mode, cg_rtol=args.cg_rtol, want_theta=True,
-                        want_fitted=True, raise_on_nonconvergence=False)
+                        want_fitted=True, raise_on_nonconvergence=False, precond=precond)
         t_e2e = time.perf_counter() - t0
         if dist:
             import torch
@@ -285,7 +291,9 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     Nl, Rl = Nl_, R_ * Nl_ / max(1, Nfull_)   # rows scale with the slab
     sb = stage_bytes(Nl, Rl, esz)
-    performed = {"zu": passes, "cg_init": passes, "cg_step": inner, "cg_update": inner}
+    if args.precond == "cheb1":
+        sb["cg_step"], sb["cg_update"] = sb["cg_step_z"], sb["cg_update_p"]
+    performed = {"zu": passes, "cg_init": passes, "cg_step": inner, "cg_update": inner, "cg_prec": inner}
     stages = {}
     for k, (ms, cnt) in prof.items():
         if k not in sb or cnt == 0 or performed[k] == 0:
@@ -301,7 +309,8 @@ def run_ours(args):
                 "share_of_step": stages[dom]["total_ms"] / (dev_s * 1e3)}
     # whole-pass algorithmic bytes: (2R+3N) + 12 N J
     J = inner / max(1, passes)
-    b_iter = esz * ((2 * Rl + 3 * Nl) + 12 * Nl * J)
+    b_iter = esz * ((2 * Rl + 3 * Nl) + 12 * Nl * J)      # SURVEY 8(d) accounting (classical CG: 12 N per inner iteration)
+    b_moved = sb["zu"] + sb["cg_init"] + J * (sb["cg_step"] + sb["cg_update"] + (sb["cg_prec"] if args.precond == "cheb1" else 0))
     line = {
         "metric": "mesh_vertex_updates_per_sec", "value": N * passes / dev_s, "unit": "vertex-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / passes,
@@ -309,10 +318,12 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": wl["desc"] + (" per GPU (weak: last axis x%d)" % world if world > 1 and args.scaling == "weak" else ""),
                    "mesh": m, "n_points": n * (world if args.scaling == "weak" else 1), "mode": mode, "lambda": args.lam,
-                   "cg_rtol": args.cg_rtol, "precond": "jacobi", "parallelism": "slab%d" % world,
+                   "cg_rtol": args.cg_rtol, "precond": args.precond, "parallelism": "slab%d" % world,
                    "l2": "working set per pass (u: %.2f GB) exceeds the 126 MB L2" % (2 * Rl * esz / 1e9)},
         "admm_iters_per_sec": passes / dev_s, "inner_cg_iters_per_pass": J,
         "pass_alg_bytes": b_iter, "pass_gbs": b_iter / (dev_s / passes) / 1e9, "pass_frac_of_peak": b_iter / (dev_s / passes) / 1e9 / peak,
+        "pass_kernel_bytes": b_moved, "pass_kernel_gbs": b_moved / (dev_s / passes) / 1e9,
+        "pass_kernel_frac_of_peak": b_moved / (dev_s / passes) / 1e9 / peak,
         "wall_seconds": wall, "device_seconds": dev_s, "gen_seconds": t_gen,
         "clocks": clocks, "gpu_launches": launches, "roofline": roof, "stages": stages, "e2e": e2e,
     }
@@ -337,6 +348,7 @@ def main():
     ap.add_argument("--mode", default="rcpp", choices=["rcpp", "cpp", "py"])
     ap.add_argument("--lam", type=float, default=1.0)
     ap.add_argument("--cg-rtol", dest="cg_rtol", type=float, default=1e-13)
+    ap.add_argument("--precond", default="cheb1", choices=["cheb1", "jacobi"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

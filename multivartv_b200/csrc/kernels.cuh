@@ -215,6 +215,8 @@ struct PeerTab {
   unsigned long long *hflag_at_prev, *hflag_at_next;      // halo-ready flags we RAISE in the neighbours' buffers
   unsigned long long *hflag_from_prev, *hflag_from_next;  // ... and the ones we WAIT on in our own buffer
   void *rghost_at_prev, *rghost_at_next;      // the neighbours' ghost planes of r that this rank fills
+  void *zghost_at_prev, *zghost_at_next;      // ... and of z (polynomial preconditioner)
+  unsigned long long *zflag_at_prev, *zflag_at_next, *zflag_from_prev, *zflag_from_next;
   int *error;                                 // set when a wait times out (a peer died): results become NaN
 };
 
@@ -284,7 +286,11 @@ struct CgArgs {
   double rtol2;    // cg_rtol^2
   const PeerTab *peer;          // non-null: peer-memory collectives (world > 1, CUDA IPC available)
   unsigned long long seq_red;   // reduction event id this launch posts / commits
-  unsigned long long seq_halo;  // version of r's ghost planes this launch posts (init, update) or needs (step)
+  unsigned long long seq_halo;  // version of r's ghost planes this launch posts (init, update) or needs (step / prec)
+  unsigned long long seq_zhalo; // version of z's ghost planes (polynomial preconditioner: prec posts, step needs)
+  T *z;            // polynomial preconditioner: z = P(D^-1 M) D^-1 r (ghosted slab)
+  double pc0, pc1; // z = pc0*z0 + pc1*D^-1 M z0,  z0 = D^-1 r
+  int prec;        // 0: Jacobi (z = D^-1 r formed on the fly), 1: degree-1 Chebyshev polynomial in D^-1 M
 };
 
 __device__ __forceinline__ bool cg_done(const double *S, double rtol2) {
@@ -304,6 +310,18 @@ __device__ __forceinline__ void cg_commit_update(double *S, const double *r2) {
   const int nxt = (((int)S[CS_ITERS]) & 1) ^ 1;
   S[2 * nxt] = r2[0];
   S[2 * nxt + 1] = r2[1];
+  S[CS_ITERS] += 1.0;
+}
+
+// polynomial-preconditioner variants: r.z comes from the prec kernel (slot of the CURRENT parity), the update only
+// delivers r.r and advances the iteration count
+__device__ __forceinline__ void cg_commit_rz(double *S, const double *r1) {
+  const int cur = ((int)S[CS_ITERS]) & 1;
+  S[2 * cur] = r1[0];
+}
+__device__ __forceinline__ void cg_commit_update_prec(double *S, const double *r1) {
+  const int nxt = (((int)S[CS_ITERS]) & 1) ^ 1;
+  S[2 * nxt + 1] = r1[0];
   S[CS_ITERS] += 1.0;
 }
 
@@ -424,7 +442,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-template <typename T, typename Cfg>
+// MODE: what the staged arrays are and what leaves the kernel
+//   STEP_JACOBI  stage r, dinv, p_old : p = dinv.*r + beta*p_old ; writes p, q = M p ; reduces p.q
+//   STEP_Z       stage z, p_old       : p = z + beta*p_old       ; writes p, q = M p ; reduces p.q
+//   STEP_PREC    stage r, dinv        : z0 = dinv.*r ; writes z = pc0*z0 + pc1*dinv.*(M z0) ; reduces r.z
+enum { STEP_JACOBI = 0, STEP_Z = 1, STEP_PREC = 2 };
+
+template <typename T, typename Cfg, int MODE>
 __global__ void __launch_bounds__(Cfg::NT)
 k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
           const RedBuf rb, const int zchunk) {
@@ -440,11 +464,11 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   const int tid = threadIdx.x;
   const int it = (int)a.S[CS_ITERS];
   const int cur = it & 1;
-  const bool first = (it == 0);
+  const bool first = (MODE == STEP_PREC) ? true : (it == 0);   // "first": no p_old term
   const T beta = first ? T(0) : (T)(a.S[2 * cur] / a.S[2 * (cur ^ 1)]);
   const T *__restrict__ p_in = a.pbuf[cur];
   T *__restrict__ p_out = a.pbuf[cur ^ 1];
-  const T *__restrict__ rr = a.r;
+  const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : a.r;     // first staged array
   const T *__restrict__ dinv = a.dinv;
   const T rhoM = (T)a.rhoM;
 
@@ -485,10 +509,13 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   const int zlo = dt.has_lo ? -1 : 0;          // lowest / highest local plane that holds real data
   const int zhi = dt.has_hi ? dt.nz : dt.nz - 1;
   const int zfirst = zc0 - 1, zlast = zc1;     // planes consumed by this CTA
-  if (a.peer) {  // the neighbours fill our ghost planes of r directly: wait for the version this iteration needs
+  if (a.peer) {  // the neighbours fill our ghost planes of r (z) directly: wait for the version this launch needs
     if (tid == 0) {
-      if (zc0 == 0 && dt.has_lo) peer_spin(a.peer->hflag_from_prev, a.seq_halo, a.peer->error);
-      if (zc1 == dt.nz && dt.has_hi) peer_spin(a.peer->hflag_from_next, a.seq_halo, a.peer->error);
+      const unsigned long long need = (MODE == STEP_Z) ? a.seq_zhalo : a.seq_halo;
+      const unsigned long long *fp = (MODE == STEP_Z) ? a.peer->zflag_from_prev : a.peer->hflag_from_prev;
+      const unsigned long long *fn = (MODE == STEP_Z) ? a.peer->zflag_from_next : a.peer->hflag_from_next;
+      if (zc0 == 0 && dt.has_lo) peer_spin(fp, need, a.peer->error);
+      if (zc1 == dt.nz && dt.has_hi) peer_spin(fn, need, a.peer->error);
     }
     __syncthreads();
   }
@@ -505,7 +532,7 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
         if (e < TE) {
           const long long idx = pb + src[k];
           cp_async<sizeof(T)>(dst + e, rr + idx);
-          cp_async<sizeof(T)>(dst + TE + e, dinv + idx);
+          if (MODE != STEP_Z) cp_async<sizeof(T)>(dst + TE + e, dinv + idx);
           if (!first) cp_async<sizeof(T)>(dst + 2 * TE + e, p_in + idx);
         }
       }
@@ -519,6 +546,7 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   const int tw = tid / (TXT * (TY / RY));
   T A0[XO][RY], A1[XO][RY], A2[XO][RY], pcp[XO][RY];
   T cq0[XO][RY], cq1[XO][RY], cq2[XO][RY];   // diag(c) of the planes retiring now / next / after next
+  T rcp[XO][RY], dcp[XO][RY], rcn[XO][RY], dcn[XO][RY];  // STEP_PREC: r and dinv at the outputs of the planes retiring next / after
   long long oidx[XO][RY];                    // in-plane offset of each output, -1 outside the mesh
 #pragma unroll
   for (int i = 0; i < XO; ++i)
@@ -526,6 +554,7 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
     for (int j = 0; j < RY; ++j) {
       A0[i][j] = A1[i][j] = A2[i][j] = pcp[i][j] = T(0);
       cq0[i][j] = cq1[i][j] = cq2[i][j] = T(0);
+      rcp[i][j] = dcp[i][j] = rcn[i][j] = dcn[i][j] = T(0);
       const int gx = x0 + tx + i * TXT, gy = y0 + yb * RY + j, gw = w0 + tw;
       oidx[i][j] = (gx < m0 && gy < m1 && gw < m2) ? gx + (long long)m0 * (gy + (long long)m1 * gw) : -1;
     }
@@ -561,11 +590,23 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
       for (int k = 0; k < NE; ++k) {
         const int e = tid + k * NT;
         if (e < TE) {
-          T v = stg[TE + e] * stg[e];
+          T v = (MODE == STEP_Z) ? stg[e] : stg[TE + e] * stg[e];
           if (!first) v += beta * stg[2 * TE + e];
           pn[e] = v;
-          if (own && wr[k]) p_out[pb + src[k]] = v;
+          if (MODE != STEP_PREC && own && wr[k]) p_out[pb + src[k]] = v;
         }
+      }
+      if (MODE == STEP_PREC) {
+        // r and dinv of plane zz at this thread's outputs, straight from the ring stage -- read BEFORE the barrier:
+        // after it, faster threads refill this stage with plane zz + DEPTH
+#pragma unroll
+        for (int i = 0; i < XO; ++i)
+#pragma unroll
+          for (int j = 0; j < RY; ++j) {
+            const int e0 = (tx + i * TXT + 1) + EX * (((Q >= 2) ? yb * RY + j + 1 : 0) + EY * ((Q >= 3) ? tw + 1 : 0));
+            rcn[i][j] = stg[e0];
+            dcn[i][j] = stg[TE + e0];
+          }
       }
     }
     __syncthreads();
@@ -612,9 +653,25 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
           if (oidx[i][j] >= 0) {
             const T pv = pcp[i][j];
             const T qv = cq0[i][j] * pv + rhoM * A0[i][j];
-            a.q[pb + oidx[i][j]] = qv;
-            red[0] += (double)pv * (double)qv;
+            if (MODE == STEP_PREC) {
+              const T zv = (T)a.pc0 * pv + (T)a.pc1 * (dcp[i][j] * qv);
+              a.z[pb + oidx[i][j]] = zv;
+              if (a.peer) {  // fill the neighbours' ghost planes of z
+                if (zz - 1 == 0 && dt.has_lo) { ((T *)a.peer->zghost_at_prev)[oidx[i][j]] = zv; __threadfence_system(); }
+                if (zz - 1 == dt.nz - 1 && dt.has_hi) { ((T *)a.peer->zghost_at_next)[oidx[i][j]] = zv; __threadfence_system(); }
+              }
+              red[0] += (double)rcp[i][j] * (double)zv;
+            } else {
+              a.q[pb + oidx[i][j]] = qv;
+              red[0] += (double)pv * (double)qv;
+            }
           }
+    }
+    if (MODE == STEP_PREC) {
+#pragma unroll
+      for (int i = 0; i < XO; ++i)
+#pragma unroll
+        for (int j = 0; j < RY; ++j) { rcp[i][j] = rcn[i][j]; dcp[i][j] = dcn[i][j]; }
     }
 #pragma unroll
     for (int i = 0; i < XO; ++i)
@@ -629,12 +686,20 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
       }
   }
   cp_async_wait<0>();
-  double *dstp = a.raw ? a.raw : (a.S + CS_PQ);
+  double *S = a.S, *raw = a.raw;
   const PeerTab *peer = a.peer;
-  const unsigned long long sr = a.seq_red;
-  grid_reduce<1, 1>(red, rb, [dstp, peer, sr](const double (&res)[1]) {
-    if (peer) peer_post(*peer, sr, res, 1);
-    else dstp[0] = res[0];
+  const unsigned long long sr = a.seq_red, sz = a.seq_zhalo;
+  grid_reduce<1, 1>(red, rb, [S, raw, peer, sr, sz](const double (&res)[1]) {
+    if (peer) {
+      if (MODE == STEP_PREC) {
+        __threadfence_system();
+        if (peer->has_lo) st_release_sys(peer->zflag_at_prev, sz);
+        if (peer->has_hi) st_release_sys(peer->zflag_at_next, sz);
+      }
+      peer_post(*peer, sr, res, 1);
+    } else if (raw) raw[0] = res[0];
+    else if (MODE == STEP_PREC) cg_commit_rz(S, res);
+    else S[CS_PQ] = res[0];
   });
 }
 
@@ -661,7 +726,7 @@ k_cg_update(const CgArgs<T> a, const long long plane, const long long nloc, cons
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const long long j = i + k * stride;
-      pv[k] = p[j]; qv[k] = q[j]; rv[k] = r[j]; xv[k] = x[j]; dv[k] = dinv[j];
+      pv[k] = p[j]; qv[k] = q[j]; rv[k] = r[j]; xv[k] = x[j]; dv[k] = a.prec ? T(0) : dinv[j];
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -681,20 +746,22 @@ k_cg_update(const CgArgs<T> a, const long long plane, const long long nloc, cons
     r[i] = rn;
     if (gprev && i < plane) { gprev[i] = rn; stored_peer = true; }
     if (gnext && i >= nloc - plane) { gnext[i - (nloc - plane)] = rn; stored_peer = true; }
-    red[0] += (double)rn * (double)(rn * dinv[i]);
+    if (!a.prec) red[0] += (double)rn * (double)(rn * dinv[i]);
     red[1] += (double)rn * (double)rn;
   }
   if (stored_peer) __threadfence_system();
   double *S = a.S, *raw = a.raw;
   const PeerTab *peer = a.peer;
   const unsigned long long sr = a.seq_red, sh = a.seq_halo;
-  grid_reduce<2, 2>(red, rb, [S, raw, peer, sr, sh](const double (&res)[2]) {
+  const int prec = a.prec;
+  grid_reduce<2, 2>(red, rb, [S, raw, peer, sr, sh, prec](const double (&res)[2]) {
     if (peer) {
       __threadfence_system();
       if (peer->has_lo) st_release_sys(peer->hflag_at_prev, sh);
       if (peer->has_hi) st_release_sys(peer->hflag_at_next, sh);
       peer_post(*peer, sr, res, 2);
     } else if (raw) { raw[0] = res[0]; raw[1] = res[1]; }
+    else if (prec) cg_commit_update_prec(S, res + 1);
     else cg_commit_update(S, res);
   });
 }
@@ -716,6 +783,27 @@ __global__ void k_cg_peer_commit_update(double *S, const PeerTab *peer, unsigned
   double v[2];
   peer_wait_sum(*peer, seq, v, 2);
   cg_commit_update(S, v);
+}
+
+__global__ void k_cg_peer_commit_rz(double *S, const PeerTab *peer, unsigned long long seq, double rtol2) {
+  if (cg_done(S, rtol2)) return;
+  double v[1];
+  peer_wait_sum(*peer, seq, v, 1);
+  cg_commit_rz(S, v);
+}
+__global__ void k_cg_peer_commit_update_prec(double *S, const PeerTab *peer, unsigned long long seq, double rtol2) {
+  if (cg_done(S, rtol2)) return;
+  double v[2];
+  peer_wait_sum(*peer, seq, v, 2);
+  cg_commit_update_prec(S, v + 1);
+}
+__global__ void k_cg_commit_rz(double *S, const double *raw, double rtol2) {
+  if (cg_done(S, rtol2)) return;
+  cg_commit_rz(S, raw);
+}
+__global__ void k_cg_commit_update_prec(double *S, const double *raw, double rtol2) {
+  if (cg_done(S, rtol2)) return;
+  cg_commit_update_prec(S, raw + 1);
 }
 
 // multi-GPU commits (after the all-reduce of `raw`)

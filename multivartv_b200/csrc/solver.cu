@@ -107,7 +107,7 @@ struct mvtv_plan {
 
   // device state (element type = dtype)
   void *theta = nullptr, *xold = nullptr, *v1 = nullptr, *v2 = nullptr, *oty = nullptr, *cnt = nullptr;
-  void *r = nullptr, *q = nullptr, *dinv = nullptr;
+  void *r = nullptr, *q = nullptr, *dinv = nullptr, *zbuf = nullptr;
   void *pbuf[2] = {nullptr, nullptr};
   double dinv_rho = NAN;  // rhoM the inverse diagonal was built for
   void *u[2] = {nullptr, nullptr};
@@ -133,11 +133,13 @@ struct mvtv_plan {
   size_t staging_bytes = 0;
   long long launches = 0;
   int last_cg_iters = 8;
+  int last_cg_prec = 0;
   // peer-memory collectives of the CG loop (CUDA IPC); falls back to NCCL when unavailable or MVTV_COMM=nccl
   unsigned char *cb = nullptr;          // this rank's comm buffer (slots, flags, halo flags, error word)
   PeerTab *d_peer = nullptr;            // device copy of the peer table, nullptr = NCCL path
   std::vector<void *> ipc_opened;
-  unsigned long long red_seq = 0, halo_seq = 0;
+  unsigned long long red_seq = 0, halo_seq = 0, zhalo_seq = 0;
+  double cheb_bmax = 0.0;   // bound on the spectrum of D^-1 (diag(c) + s D^T D), independent of s and c
   int zu_variant = -1;   // ZV_* when the compile-time block tables of k_zu_march match this plan, else -1 (gather kernel)
 
   // optional per-kernel-class CUDA-event timing on the plan's stream (mvtv_plan_profile)
@@ -205,7 +207,7 @@ struct mvtv_plan {
     if (cb) cudaFree(cb);
     if (d_peer) cudaFree(d_peer);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pbuf[0], pbuf[1], q, dinv, u[0], u[1], S, zr, raw, partials, counters, vid, staging};
+    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pbuf[0], pbuf[1], q, dinv, zbuf, u[0], u[1], S, zr, raw, partials, counters, vid, staging};
     for (void *b : bufs)
       if (b) cudaFree(b);
     if (h_scal) cudaFreeHost(h_scal);
@@ -334,6 +336,36 @@ struct mvtv_plan {
       }
       st.diagK[cls] = dsum;
     }
+    // Gershgorin bound on spec(D^-1 M), M = diag(c) + s K: the row of K at a vertex of boundary class cls is the
+    // stencil with the offsets that leave the mesh folded back onto the clamped neighbour; (c + s*rowabs)/(c + s*diag)
+    // is largest at c = 0, so the bound is max_cls rowabs/diag whatever c and s are.
+    cheb_bmax = 1.0;
+    for (int cls = 0; cls < (1 << P); ++cls) {
+      bool possible = true;
+      for (int a = 0; a < P; ++a)
+        if (!((cls >> a) & 1) && m[a] < 3) possible = false;   // an interior vertex needs m >= 3 on that axis
+      if (!possible) continue;
+      std::vector<double> row(st.npts, 0.0);
+      for (int o = 0; o < st.npts; ++o) {
+        int rem = o, tgt = 0, mul = 1;
+        for (int a = 0; a < P; ++a) {
+          int dgt = rem % 3;
+          rem /= 3;
+          if ((cls >> a) & 1) {
+            if (m[a] < 2) dgt = 1;                 // extent-1 axis: every neighbour is the vertex itself
+            else if (dgt == 0) dgt = 1;            // low boundary: the -1 neighbour folds onto the vertex
+          }
+          tgt += dgt * mul;
+          mul *= 3;
+        }
+        row[tgt] += st.coef[o];
+      }
+      int centre = 0, mul = 1;
+      for (int a = 0; a < P; ++a) { centre += mul; mul *= 3; }
+      double rowabs = 0.0;
+      for (double v : row) rowabs += fabs(v);
+      if (row[centre] > 0.0) cheb_bmax = std::max(cheb_bmax, rowabs / row[centre]);
+    }
   }
 
   void allocate() {
@@ -342,7 +374,7 @@ struct mvtv_plan {
     MVTV_CUDA(cudaEventCreate(&ev0));
     MVTV_CUDA(cudaEventCreate(&ev1));
     const size_t vb = (size_t)dt.usz * esz();
-    void **vecs[] = {&theta, &xold, &v1, &v2, &oty, &cnt, &r, &pbuf[0], &pbuf[1], &q, &dinv};
+    void **vecs[] = {&theta, &xold, &v1, &v2, &oty, &cnt, &r, &pbuf[0], &pbuf[1], &q, &dinv, &zbuf};
     for (void **v : vecs) {
       MVTV_CUDA(cudaMalloc(v, vb));
       MVTV_CUDA(cudaMemsetAsync(*v, 0, vb, stream));
@@ -401,13 +433,14 @@ struct mvtv_plan {
     if (world < 2 || world > MVTV_PEER_MAXW || (env && std::string(env) == "nccl")) return;
     const size_t n_slots = (size_t)MVTV_PEER_NSLOT * MVTV_PEER_MAXW * MVTV_PEER_NVAL;   // doubles
     const size_t n_flags = (size_t)MVTV_PEER_NSLOT * MVTV_PEER_MAXW;                    // u64
-    const size_t cb_bytes = 8 * (n_slots + n_flags + 2 + 1);
+    const size_t cb_bytes = 8 * (n_slots + n_flags + 4 + 1);
     MVTV_CUDA(cudaMalloc(&cb, cb_bytes));
     MVTV_CUDA(cudaMemset(cb, 0, cb_bytes));
-    struct Handles { cudaIpcMemHandle_t cb, r; };
-    static_assert(sizeof(Handles) == 128, "two 64-byte IPC handles");
+    struct Handles { cudaIpcMemHandle_t cb, r, z; };
+    static_assert(sizeof(Handles) == 192, "three 64-byte IPC handles");
     Handles mine;
-    bool ok = cudaIpcGetMemHandle(&mine.cb, cb) == cudaSuccess && cudaIpcGetMemHandle(&mine.r, r) == cudaSuccess;
+    bool ok = cudaIpcGetMemHandle(&mine.cb, cb) == cudaSuccess && cudaIpcGetMemHandle(&mine.r, r) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.z, zbuf) == cudaSuccess;
     // all ranks must take the same decision: all-reduce the ok flag with the handles' exchange
     unsigned char *d_h = nullptr;
     MVTV_CUDA(cudaMalloc(&d_h, sizeof(Handles) * world + 8));
@@ -417,7 +450,7 @@ struct mvtv_plan {
     MVTV_CUDA(cudaStreamSynchronize(stream));
     MVTV_CUDA(cudaMemcpy(all.data(), d_h, sizeof(Handles) * world, cudaMemcpyDeviceToHost));
     std::vector<unsigned char *> pcb(world, nullptr);
-    unsigned char *r_prev = nullptr, *r_next = nullptr;
+    unsigned char *r_prev = nullptr, *r_next = nullptr, *z_prev = nullptr, *z_next = nullptr;
     for (int j = 0; ok && j < world; ++j) {
       if (j == rank) { pcb[j] = cb; continue; }
       void *p = nullptr;
@@ -429,6 +462,10 @@ struct mvtv_plan {
         if (cudaIpcOpenMemHandle(&pr, all[j].r, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
         ipc_opened.push_back(pr);
         (j == rank - 1 ? r_prev : r_next) = (unsigned char *)pr;
+        void *pz = nullptr;
+        if (cudaIpcOpenMemHandle(&pz, all[j].z, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+        ipc_opened.push_back(pz);
+        (j == rank - 1 ? z_prev : z_next) = (unsigned char *)pz;
       }
     }
     cudaGetLastError();
@@ -462,7 +499,13 @@ struct mvtv_plan {
     auto nz_of = [&](int j) { return basez + (j < extra ? 1 : 0); };
     pt.rghost_at_prev = dt.has_lo ? (void *)(r_prev + esz() * (size_t)((nz_of(rank - 1) + 1) * dt.plane)) : nullptr;
     pt.rghost_at_next = dt.has_hi ? (void *)r_next : nullptr;
-    pt.error = (int *)(cb + 8 * (n_slots + n_flags + 2));
+    pt.zghost_at_prev = dt.has_lo ? (void *)(z_prev + esz() * (size_t)((nz_of(rank - 1) + 1) * dt.plane)) : nullptr;
+    pt.zghost_at_next = dt.has_hi ? (void *)z_next : nullptr;
+    pt.zflag_from_prev = hflags_of(cb) + 2;
+    pt.zflag_from_next = hflags_of(cb) + 3;
+    pt.zflag_at_prev = dt.has_lo ? hflags_of(pcb[rank - 1]) + 3 : nullptr;
+    pt.zflag_at_next = dt.has_hi ? hflags_of(pcb[rank + 1]) + 2 : nullptr;
+    pt.error = (int *)(cb + 8 * (n_slots + n_flags + 4));
     MVTV_CUDA(cudaMalloc(&d_peer, sizeof(PeerTab)));
     MVTV_CUDA(cudaMemcpy(d_peer, &pt, sizeof(PeerTab), cudaMemcpyHostToDevice));
   }
@@ -520,7 +563,7 @@ struct mvtv_plan {
 
   // ---- the ADMM loop ---------------------------------------------------------------------------
   template <typename T, int P>
-  int cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, long long &inner, int &status);
+  int cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, int prec, long long &inner, int &status);
   template <typename T>
   void launch_zu(double kappa, double usc, int mode, int init, bool with_prev);
   template <typename T, typename Cfg, int V>
@@ -708,7 +751,7 @@ template <> struct StepShape<3> { using Cfg = StepCfg<2,  32, 1, 16, 4, 1, 4>; }
 template <> struct StepShape<4> { using Cfg = StepCfg<3,  32, 1,  8, 2, 4, 3>; };   // 32x8x4 tile, 512 threads, 163 KB
 
 template <typename T, int P>
-int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, long long &inner, int &status) {
+int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, int prec, long long &inner, int &status) {
   using Cfg = typename StepShape<P>::Cfg;
   constexpr int Q = P - 1;
   if (!(dinv_rho == rhoM)) {
@@ -734,6 +777,16 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   a.peer = d_peer;
   a.seq_red = 0;
   a.seq_halo = 0;
+  a.seq_zhalo = 0;
+  a.z = (T *)zbuf;
+  a.prec = prec;
+  {
+    // degree-1 polynomial in D^-1 M whose residual 1 - t P(t) is the Chebyshev polynomial T2 on [bmax/30, bmax]
+    const double b = cheb_bmax, lo = b / 30.0, th = 0.5 * (b + lo), de = 0.5 * (b - lo);
+    const double T2 = 2.0 * (th / de) * (th / de) - 1.0;
+    a.pc0 = 4.0 * th / (de * de * T2);
+    a.pc1 = -2.0 / (de * de * T2);
+  }
   a.rho = rho;
   a.uscale = usc;
   a.rhoM = rhoM;
@@ -762,8 +815,10 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   static bool attr_set = false;
   static int occ = 1;
   if (!attr_set) {
-    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step<T, Cfg>, Cfg::NT, smem));
+    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_JACOBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step<T, Cfg, STEP_JACOBI>, Cfg::NT, smem));
     if (occ < 1) occ = 1;
     attr_set = true;
   }
@@ -793,9 +848,25 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   for (;;) {
     for (int k = 0; k < batch; ++k) {
       if (world > 1 && !d_peer) exchange_ghosts<T>((T *)r);
+      if (prec) {  // z = P(D^-1 M) D^-1 r and r.z
+        a.seq_red = ++red_seq;
+        a.seq_zhalo = ++zhalo_seq;
+        prof_begin(MVTV_KC_CG_PREC);
+        k_cg_step<T, Cfg, STEP_PREC><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk);
+        prof_end();
+        if (d_peer) {
+          k_cg_peer_commit_rz<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
+        } else if (world > 1) {
+          allreduce(raw, 1, ncclSum);
+          k_cg_commit_rz<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
+          exchange_ghosts<T>((T *)zbuf);
+        }
+        launches += world > 1 ? 2 : 1;
+      }
       a.seq_red = ++red_seq;       // a.seq_halo: the version the last producer of r posted
       prof_begin(MVTV_KC_CG_STEP);
-      k_cg_step<T, Cfg><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+      if (prec) k_cg_step<T, Cfg, STEP_Z><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+      else k_cg_step<T, Cfg, STEP_JACOBI><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       prof_end();
       if (d_peer) {
         k_cg_peer_commit_pq<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
@@ -809,10 +880,12 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       k_cg_update<T><<<gu, 256, 0, stream>>>(a, dt.plane, dt.Nloc, RedBuf{partials, counters + 3});
       prof_end();
       if (d_peer) {
-        k_cg_peer_commit_update<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
+        if (prec) k_cg_peer_commit_update_prec<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
+        else k_cg_peer_commit_update<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
       } else if (world > 1) {
         allreduce(raw, 2, ncclSum);
-        k_cg_commit_update<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
+        if (prec) k_cg_commit_update_prec<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
+        else k_cg_commit_update<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
       }
       launches += world > 1 ? 4 : 2;
     }
@@ -946,8 +1019,8 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
                           : (mode == MVTV_MODE_CPP ? 2000 : (mode == MVTV_MODE_RCPP ? 3000 : 5000));
   const double cg_rtol = prm.cg_rtol > 0.0 ? prm.cg_rtol : (dtype == MVTV_F64 ? 1e-13 : 1e-5);
   const int cg_maxit = prm.cg_maxit > 0 ? prm.cg_maxit : (dtype == MVTV_F64 ? 20000 : 1000);
-  if (prm.precond != MVTV_PRECOND_JACOBI)
-    throw Error(MVTV_ERR_UNSUPPORTED, "only MVTV_PRECOND_JACOBI is implemented");
+  if (prm.precond != MVTV_PRECOND_JACOBI && prm.precond != MVTV_PRECOND_CHEB1 && prm.precond != MVTV_PRECOND_AUTO)
+    throw Error(MVTV_ERR_UNSUPPORTED, "precond must be MVTV_PRECOND_JACOBI, _CHEB1 or _AUTO");
   const long long launches0 = launches;
   const long long nvec = dt.usz;
   T *th = (T *)theta;
@@ -1017,10 +1090,15 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
     if (prm.max_passes > 0 && passes >= prm.max_passes) break;
     // b = Oty + rho*Dt*(alpha+u) ; theta = spsolve(sp_crosses, b)     cpp :115-116 / rcpp :112-113
     int cgst = MVTV_OK;
+    // AUTO: the polynomial pays off once plain Jacobi-PCG needs more than ~24 iterations (it halves the iteration
+    // count for one more stencil each); the estimate comes from the previous x-update on this plan
+    const double jac_equiv = last_cg_prec ? 1.9 * last_cg_iters : (double)last_cg_iters;
+    const int prec = (prm.precond == MVTV_PRECOND_CHEB1) ? 1 : (prm.precond == MVTV_PRECOND_AUTO ? (jac_equiv > 24.0) : 0);
+    last_cg_prec = prec;
     switch (dt.P) {
-      case 2: cg_solve<T, 2>(rho, uscale, rhoM, cg_rtol, cg_maxit, inner, cgst); break;
-      case 3: cg_solve<T, 3>(rho, uscale, rhoM, cg_rtol, cg_maxit, inner, cgst); break;
-      case 4: cg_solve<T, 4>(rho, uscale, rhoM, cg_rtol, cg_maxit, inner, cgst); break;
+      case 2: cg_solve<T, 2>(rho, uscale, rhoM, cg_rtol, cg_maxit, prec, inner, cgst); break;
+      case 3: cg_solve<T, 3>(rho, uscale, rhoM, cg_rtol, cg_maxit, prec, inner, cgst); break;
+      case 4: cg_solve<T, 4>(rho, uscale, rhoM, cg_rtol, cg_maxit, prec, inner, cgst); break;
       default: throw Error(MVTV_ERR_UNSUPPORTED, "p must be 1..4");
     }
     if (cgst != MVTV_OK) { status = cgst; break; }

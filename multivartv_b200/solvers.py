@@ -15,7 +15,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import (F32, F64, MODE_CPP, MODE_PY, MODE_RCPP, PRECOND_JACOBI, VARIANT_INTENDED,  # noqa: F401
+from ._lib import (F32, F64, MODE_CPP, MODE_PY, MODE_RCPP, PRECOND_AUTO, PRECOND_CHEB1, PRECOND_JACOBI, VARIANT_INTENDED,  # noqa: F401
                    VARIANT_REFERENCE, WARM_THETA_FROM_PLAN, WARM_U_FROM_PLAN, MvtvError, NotConverged)
 
 _MODES = {"cpp": MODE_CPP, "rcpp": MODE_RCPP, "py": MODE_PY, MODE_CPP: MODE_CPP, MODE_RCPP: MODE_RCPP,
@@ -230,7 +230,7 @@ class Plan:
 
     # -- the hot path ------------------------------------------------------------------------
     def solve(self, lam, mode="cpp", theta_init=None, u_init=None, rho_init=None, rho_matrix0=None, tol=None,
-              max_counter=0, max_passes=0, cg_rtol=0.0, cg_maxit=0, precond=PRECOND_JACOBI, flags=0,
+              max_counter=0, max_passes=0, cg_rtol=0.0, cg_maxit=0, precond=PRECOND_AUTO, flags=0,
               want_u=False, want_fitted=True, want_theta=True, raise_on_nonconvergence=True):
         L = _lib.load()
         mode = _MODES[mode]
@@ -268,7 +268,7 @@ class Plan:
                     kernel_launches=int(res.kernel_launches))
 
     def solve_path(self, lambdas, ftrue, mode="cpp", tol=None, max_counter=0, cg_rtol=0.0, cg_maxit=0,
-                   rho_init=None, want_thetas=False, want_best=True):
+                   rho_init=None, want_thetas=False, want_best=True, precond=PRECOND_AUTO):
         """mbs_path (cpp-code/solvers.cpp:196-217 ; rcpp solvers.cpp:204-222): warm-started lambda path that stays
         on the device between lambdas.  Returns MSEs, Counters and the first minimum-MSE model."""
         L = _lib.load()
@@ -283,6 +283,7 @@ class Plan:
         prm.rho_matrix0 = math.nan
         prm.tol = math.nan if tol is None else float(tol)
         prm.max_counter, prm.cg_rtol, prm.cg_maxit = int(max_counter), float(cg_rtol), int(cg_maxit)
+        prm.precond = int(precond)
         nl = lambdas.size
         mses = np.empty(nl)
         counters = np.zeros(nl, dtype=np.int32)

@@ -29,9 +29,13 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    cases = [([24, 22], 3000, "rcpp", 1.0, 0), ([24, 22], 3000, "cpp", 3.0, 0), ([12, 12, 13], 4000, "rcpp", 0.7, 0),
-             ([8, 8, 8, 9], 5000, "rcpp", 1.0, 25), ([64, 64], 20000, "py", 0.8, 0), ([40, 40, 40], 64000, "rcpp", 1.0, 15)]
-    for dims, n, mode, lam, max_passes in cases:
+    J, C1 = mv.PRECOND_JACOBI, mv.PRECOND_CHEB1
+    cases = [([24, 22], 3000, "rcpp", 1.0, 0, J), ([24, 22], 3000, "cpp", 3.0, 0, J), ([12, 12, 13], 4000, "rcpp", 0.7, 0, J),
+             ([8, 8, 8, 9], 5000, "rcpp", 1.0, 25, J), ([64, 64], 20000, "py", 0.8, 0, J),
+             ([40, 40, 40], 64000, "rcpp", 1.0, 15, J), ([24, 22], 3000, "rcpp", 1.0, 0, C1),
+             ([12, 12, 13], 4000, "rcpp", 0.7, 0, C1), ([8, 8, 8, 9], 5000, "rcpp", 1.0, 25, C1),
+             ([40, 40, 40], 64000, "rcpp", 1.0, 15, C1)]
+    for dims, n, mode, lam, max_passes, precond in cases:
         p = len(dims)
         imode = {"cpp": 0, "rcpp": 1, "py": 2}[mode]
         x, y = synth(41 + p, n, p, 0.0, 1.0, 0.5)
@@ -43,7 +47,7 @@ def main():
         dist.broadcast_object_list(box, src=0)
         with mv.Plan(dims, device=local, rank=rank, world=world, nccl_unique_id=box[0]) as pl:
             pl.set_points(xo, yo, axes)
-            out = pl.solve(lam, mode=mode, max_passes=max_passes, want_fitted=False, cg_rtol=1e-13)
+            out = pl.solve(lam, mode=mode, max_passes=max_passes, want_fitted=False, cg_rtol=1e-13, precond=precond)
             gathered = [None] * world
             dist.all_gather_object(gathered, (pl.z0, out["theta"], out["counter"], out["passes"], out["inner_iters"]))
         if rank == 0:
@@ -56,8 +60,8 @@ def main():
             same = all(g[2] == ref["counter"] for g in gathered)
             good = same and err <= 1e-9
             ok = ok and good
-            print("%s dims=%s mode=%s lam=%g: Counter=%d (oracle %d) passes=%d inner=%d max|dtheta|=%.2e %s"
-                  % ("OK  " if good else "FAIL", dims, mode, lam, gathered[0][2], ref["counter"], gathered[0][3],
+            print("%s precond=%d dims=%s mode=%s lam=%g: Counter=%d (oracle %d) passes=%d inner=%d max|dtheta|=%.2e %s"
+                  % ("OK  " if good else "FAIL", precond, dims, mode, lam, gathered[0][2], ref["counter"], gathered[0][3],
                      gathered[0][4], err, ""), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)

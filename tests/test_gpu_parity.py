@@ -440,3 +440,46 @@ def test_mbs_cv_driver(mv):
     out1 = mv.mbs(x, y, m, n_lambda=6, folds=1, mode="rcpp")
     assert len(out1["models"]) == 6 and out1["lambda_minmse_ind"] == int(np.argmin(out1["cv.mses"])) + 1
     assert np.isfinite(out1["theta_hat"]).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# polynomial preconditioner (MVTV_PRECOND_CHEB1): same fixed points, fewer inner iterations
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["cpp", "rcpp", "py"])
+@pytest.mark.parametrize("dims,n", [([32, 32], 1000), ([9, 9, 9], 600), ([5, 5, 5, 5], 600), ([16], 200), ([1, 12], 200)])
+def test_cheb1_preconditioner_parity(mv, mode, dims, n):
+    imode = {"cpp": 0, "rcpp": 1, "py": 2}[mode]
+    p = len(dims)
+    x, y = synth(50 + p, n, p, 0.0, 1.0, 0.5)
+    axes = po.mesh_axes(x, dims, imode)
+    for lam in (0.5, 2.5):
+        ref = co.mbs_one(x, y, dims, axes, lam, mode=imode)
+        with mv.Plan(dims) as pl:
+            pl.set_points(x, y, axes)
+            out = pl.solve(lam, mode=mode, precond=mv.PRECOND_CHEB1)
+            base = pl.solve(lam, mode=mode, precond=mv.PRECOND_JACOBI)
+        _check(out, ref)
+        assert out["passes"] == ref["passes"]
+        assert out["inner_iters"] < base["inner_iters"] or base["inner_iters"] < 50
+
+
+def test_cheb1_midsize_and_fp32(mv):
+    dims, n = [128, 128], 16384
+    x, y = synth(61, n, 2, 0.0, 1.0, 0.5)
+    axes = po.mesh_axes(x, dims, po.MODE_RCPP)
+    ref = co.mbs_one(x, y, dims, axes, 1.0, mode=co.MODE_RCPP, max_passes=15, solver=co.SOLVER_PCG, cg_rtol=1e-13)
+    with mv.Plan(dims) as pl:
+        pl.set_points(x, y, axes)
+        out = pl.solve(1.0, mode="rcpp", max_passes=15, precond=mv.PRECOND_CHEB1)
+        base = pl.solve(1.0, mode="rcpp", max_passes=15)
+    assert np.abs(out["theta"] - ref["theta"]).max() <= FP64_TOL
+    assert out["inner_iters"] * 1.6 < base["inner_iters"]
+    rng = np.random.RandomState(3)
+    xx = rng.uniform(0, 1, (4000, 3))
+    yy = np.prod(xx > 0.5, axis=1) * 1.0 + 0.5 * rng.normal(size=4000)
+    axes = po.mesh_axes(xx, [12, 12, 12], po.MODE_RCPP)
+    ref = co.mbs_one(xx, yy, [12, 12, 12], axes, 1.0, mode=co.MODE_RCPP, max_passes=30)
+    with mv.Plan([12, 12, 12], dtype=mv.F32) as pl:
+        pl.set_points(xx, yy, axes)
+        out = pl.solve(1.0, mode="rcpp", max_passes=30, precond=mv.PRECOND_CHEB1)
+    assert np.abs(out["theta"] - ref["theta"]).max() <= FP32_TOL
