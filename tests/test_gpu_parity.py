@@ -471,8 +471,12 @@ def test_cheb1_midsize_and_fp32(mv):
     with mv.Plan(dims) as pl:
         pl.set_points(x, y, axes)
         out = pl.solve(1.0, mode="rcpp", max_passes=15, precond=mv.PRECOND_CHEB1)
-        base = pl.solve(1.0, mode="rcpp", max_passes=15)
+        base = pl.solve(1.0, mode="rcpp", max_passes=15, precond=mv.PRECOND_JACOBI)
+        auto = pl.solve(1.0, mode="rcpp", max_passes=15)          # default: MVTV_PRECOND_AUTO
+    assert np.abs(auto["theta"] - ref["theta"]).max() <= FP64_TOL
+    assert auto["inner_iters"] <= base["inner_iters"]
     assert np.abs(out["theta"] - ref["theta"]).max() <= FP64_TOL
+    assert np.abs(base["theta"] - ref["theta"]).max() <= FP64_TOL
     assert out["inner_iters"] * 1.6 < base["inner_iters"]
     rng = np.random.RandomState(3)
     xx = rng.uniform(0, 1, (4000, 3))
