@@ -282,6 +282,65 @@ inline double mse(const vec &fits, const vec &y) {  // cpp-code/solvers.cpp:160-
 }
 inline double mbs_mse(const mbs_one_object &model, const vec &y) { return mse(model.fitted, y); }
 
+// ---- lambda path and lambda grid (cpp-code/solvers.hpp:54-62,101-109) -------------------------------------
+typedef std::vector<mbs_one_object> MBSVEC;
+typedef struct mbs_object {  // cpp-code/solvers.hpp:56-62
+  mbs_one_object minmse_model;
+  MBSVEC models;
+  double minmse = 0.0;
+  double minmse_lambda = 0.0;
+  vec mses;
+} mbs_object;
+
+// lam_max_pinv (cpp-code/utils.cpp:399-404) on the cached operators, then the grid of create_lambdas
+// (cpp-code/solvers.cpp:179-192): flipud(exp(linspace(log(1e-5*lambda_max), log(lambda_max), n_lambda)))
+inline vec create_lambdas(int n_lambda, mbs_cache &inits, vec *lambdas = NULL) {
+  if (lambdas != NULL) return *lambdas;
+  double lambda_max = 0.0;
+  check(mvtv_lambda_max(inits.plan, MVTV_MODE_CPP, &lambda_max, nullptr));
+  std::printf("lambda_max = %f ", lambda_max);
+  vec out((size_t)n_lambda);
+  const double a = std::log(lambda_max * 0.00001), b = std::log(lambda_max);
+  for (int i = 0; i < n_lambda; ++i) {
+    const double t = (n_lambda == 1 || i == n_lambda - 1) ? b : a + double(i) * ((b - a) / double(n_lambda - 1));
+    out[(size_t)(n_lambda - 1 - i)] = std::exp(t);
+  }
+  return out;
+}
+
+// mbs_path (cpp-code/solvers.hpp:109 / solvers.cpp:196-217): warm-started path that stays on the device
+inline void mbs_path(const mat &data, const vec &y, const vec &m, const MAT &mesh, int n_lambda, const vec &lambdas,
+                     const vec &ftrue, mbs_object &output, mbs_cache &inits, int mode = MVTV_MODE_CPP) {
+  mvtv_solve_params p = default_params(mode, lambdas[0]);
+  mvtv_solve_result total{};
+  const size_t N = (size_t)inits.ntheta, n = (size_t)inits.n;
+  std::vector<double> thetas((size_t)n_lambda * N);
+  std::vector<int32_t> counters((size_t)n_lambda);
+  vec MSEs((size_t)n_lambda);
+  int32_t best = 0;
+  check(mvtv_solve_path(inits.plan, &p, n_lambda, lambdas.memptr(), ftrue.memptr(), MSEs.memptr(), counters.data(),
+                        nullptr, thetas.data(), nullptr, nullptr, &best, &total));
+  for (int i = 0; i < n_lambda; ++i) {
+    std::printf("Lambda = %f, Counter = %i \n", lambdas[(size_t)i], counters[(size_t)i]);
+    mbs_one_object model;
+    model.mesh = mesh;
+    model.theta_hat = vec(std::vector<double>(thetas.begin() + (size_t)i * N, thetas.begin() + (size_t)(i + 1) * N));
+    model.fitted = vec(n);
+    check(mvtv_predict(inits.plan, (int64_t)n, data.memptr(), inits.axes.data(), model.theta_hat.memptr(),
+                       model.fitted.memptr()));
+    model.data = data;
+    model.y = y;
+    model.m = m;
+    model.counter = counters[(size_t)i];
+    output.models.push_back(model);
+  }
+  // fill_output_mbs (cpp-code/solvers.cpp:170-177): first instance of the lowest MSE
+  output.minmse_model = output.models[(size_t)best];
+  output.minmse = MSEs[(size_t)best];
+  output.minmse_lambda = lambdas[(size_t)best];
+  output.mses = MSEs;
+}
+
 // ---- rcpp-code/MultivarTV/src/solvers.hpp variants ---------------------------------------------------
 namespace rcpp {
 typedef struct admm_out {  // rcpp solvers.hpp:91-95

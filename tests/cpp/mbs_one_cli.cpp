@@ -52,6 +52,19 @@ int main(int argc, char **argv) {
   vec again = mbs_predict(model, X);
   for (size_t i = 0; i < again.size(); ++i) if (again[i] != model.fitted[i]) { std::printf("predict mismatch\n"); return 1; }
 
+  if (mode == 0) {  // mbs_path (cpp-code/solvers.cpp:196-217) on a cache, written the way mbs() calls it
+    MAT mesh = create_mesh(X, m);
+    mbs_cache cache;
+    create_cache_objects(X, y, mesh, m, cache);
+    vec lambdas = {4.0, 2.0, lambda};
+    mbs_object path;
+    mbs_path(X, y, m, mesh, 3, lambdas, y, path, cache);
+    if (path.models.size() != 3 || path.mses.size() != 3) { std::printf("mbs_path size mismatch\n"); return 1; }
+    double best = path.mses[0];
+    for (size_t i = 1; i < 3; ++i) best = std::min(best, path.mses[i]);
+    if (path.minmse != best) { std::printf("minmse mismatch\n"); return 1; }
+    if (std::fabs(mse(path.models[2].fitted, y) - path.mses[2]) > 1e-12) { std::printf("path mse mismatch\n"); return 1; }
+  }
   std::ofstream out(argv[2], std::ios::binary);
   int64_t counter = model.counter, N = (int64_t)model.theta_hat.size();
   out.write((char *)&counter, 8); out.write((char *)&N, 8); out.write((char *)&n, 8);
