@@ -427,7 +427,14 @@ struct StepCfg {
   static constexpr int TE = EX * EY * EW;   // plane tile with halo
   static constexpr int NE = (TE + NT - 1) / NT;
   static constexpr int DEPTH = DEPTH_;      // cp.async ring stages
-  static constexpr int SMEM_ELEMS = (3 * DEPTH_ + 1) * TE;
+  static constexpr int SMEM_ELEMS = (3 * DEPTH_ + 1) * TE;     // STEP_JACOBI stages three arrays per plane
+  static constexpr int SMEM_ELEMS2 = (2 * DEPTH_ + 1) * TE;    // STEP_Z / STEP_PREC stage two
+  // 2-D meshes (Q == 1) run best with the three-array ring stride for every variant (fewer, longer-lived CTAs);
+  // 3-D / 4-D use the compact two-array ring for STEP_Z / STEP_PREC to fit one more CTA per SM
+  template <int MODE>
+  __host__ __device__ static constexpr int narr() { return (MODE == 0 || Q_ == 1) ? 3 : 2; }
+  template <int MODE>
+  __host__ __device__ static constexpr int smem_elems() { return (narr<MODE>() * DEPTH_ + 1) * TE; }
   static_assert(TY_ % RY_ == 0, "RY must divide TY");
   static_assert(Q_ >= 2 || (TY_ == 1 && RY_ == 1), "Q=1 has no axis 1");
   static_assert(Q_ >= 3 || TW_ == 1, "Q<3 has no axis 2");
@@ -449,7 +456,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 enum { STEP_JACOBI = 0, STEP_Z = 1, STEP_PREC = 2 };
 
 template <typename T, typename Cfg, int MODE>
-__global__ void __launch_bounds__(Cfg::NT)
+__global__ void __launch_bounds__(Cfg::NT, (Cfg::NT <= 256 ? (MODE != STEP_PREC ? 4 : 3) : 1))
 k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
           const RedBuf rb, const int zchunk) {
   if (cg_done(a.S, a.rtol2)) return;
@@ -458,8 +465,11 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   constexpr int NDY = (Q >= 2) ? 3 : 1, NDW = (Q >= 3) ? 3 : 1;   // in-plane stencil extents beyond axis 0
   constexpr int PW = 3 * NDY * NDW;                                 // stencil points per plane
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *ring = reinterpret_cast<T *>(smem_raw);   // [DEPTH][3][TE]: r, dinv, p_old
-  T *pn = ring + 3 * DEPTH * TE;               // [TE]: p_new of the plane being consumed
+  constexpr int NARR = Cfg::template narr<MODE>();     // staged arrays per plane (ring stride)
+  constexpr int SLOT_B = 1;                              // dinv (JACOBI, PREC)
+  constexpr int SLOT_C = (MODE == STEP_Z && NARR == 2) ? 1 : 2;  // p_old (JACOBI, Z)
+  T *ring = reinterpret_cast<T *>(smem_raw);   // [DEPTH][NARR][TE]: r|z, dinv, p_old
+  T *pn = ring + NARR * DEPTH * TE;            // [TE]: p_new of the plane being consumed
 
   const int tid = threadIdx.x;
   const int it = (int)a.S[CS_ITERS];
@@ -525,15 +535,15 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
     if (zz <= zlast) {
       const int zs = min(max(zz, zlo), zhi);
       const long long pb = (long long)(zs + 1) * dt.plane;
-      T *dst = ring + (size_t)((zz - zfirst) % DEPTH) * 3 * TE;
+      T *dst = ring + (size_t)((zz - zfirst) % DEPTH) * NARR * TE;
 #pragma unroll
       for (int k = 0; k < NE; ++k) {
         const int e = tid + k * NT;
         if (e < TE) {
           const long long idx = pb + src[k];
           cp_async<sizeof(T)>(dst + e, rr + idx);
-          if (MODE != STEP_Z) cp_async<sizeof(T)>(dst + TE + e, dinv + idx);
-          if (!first) cp_async<sizeof(T)>(dst + 2 * TE + e, p_in + idx);
+          if (MODE != STEP_Z) cp_async<sizeof(T)>(dst + SLOT_B * TE + e, dinv + idx);
+          if (!first) cp_async<sizeof(T)>(dst + SLOT_C * TE + e, p_in + idx);
         }
       }
     }
@@ -585,13 +595,13 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
       const int zs = min(max(zz, zlo), zhi);
       const bool own = (zz == zs) && ((zz >= zc0 && zz < zc1) || (zz < 0 && zc0 == 0) || (zz >= dt.nz && zc1 == dt.nz));
       const long long pb = (long long)(zs + 1) * dt.plane;
-      const T *stg = ring + (size_t)((zz - zfirst) % DEPTH) * 3 * TE;
+      const T *stg = ring + (size_t)((zz - zfirst) % DEPTH) * NARR * TE;
 #pragma unroll
       for (int k = 0; k < NE; ++k) {
         const int e = tid + k * NT;
         if (e < TE) {
-          T v = (MODE == STEP_Z) ? stg[e] : stg[TE + e] * stg[e];
-          if (!first) v += beta * stg[2 * TE + e];
+          T v = (MODE == STEP_Z) ? stg[e] : stg[SLOT_B * TE + e] * stg[e];
+          if (!first) v += beta * stg[SLOT_C * TE + e];
           pn[e] = v;
           if (MODE != STEP_PREC && own && wr[k]) p_out[pb + src[k]] = v;
         }
@@ -605,7 +615,7 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
           for (int j = 0; j < RY; ++j) {
             const int e0 = (tx + i * TXT + 1) + EX * (((Q >= 2) ? yb * RY + j + 1 : 0) + EY * ((Q >= 3) ? tw + 1 : 0));
             rcn[i][j] = stg[e0];
-            dcn[i][j] = stg[TE + e0];
+            dcn[i][j] = stg[SLOT_B * TE + e0];
           }
       }
     }

@@ -807,40 +807,48 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     k_cg_commit_init<<<1, 1, 0, stream>>>(S, raw);
     launches += 1;
   }
-  // fused direction + SpMV launch shape: in-plane tiles x chunks of the last axis, ~4 CTAs per SM
+  // fused direction + SpMV launch shape: in-plane tiles x chunks of the last axis.  Chunks are sized per kernel
+  // variant (their register counts, hence resident CTAs per SM, differ) to fill whole waves of (SMs x resident CTAs)
+  // while keeping chunks >= 16 planes so the two extra planes a chunk stages stay cheap.
   const int m0 = (int)dt.m[0], m1 = Q >= 2 ? (int)dt.m[1] : 1, m2 = Q >= 3 ? (int)dt.m[2] : 1;
   const unsigned tiles = (unsigned)(((m0 + Cfg::TX - 1) / Cfg::TX) * ((m1 + Cfg::TY - 1) / Cfg::TY) *
                                     ((m2 + Cfg::TW - 1) / Cfg::TW));
-  const size_t smem = sizeof(T) * (size_t)Cfg::SMEM_ELEMS;
+  const size_t smem = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_JACOBI>();
+  const size_t smem2 = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_Z>();
   static bool attr_set = false;
-  static int occ = 1;
+  static int occ3[3] = {1, 1, 1};
   if (!attr_set) {
     MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_JACOBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step<T, Cfg, STEP_JACOBI>, Cfg::NT, smem));
-    if (occ < 1) occ = 1;
+    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[STEP_JACOBI], k_cg_step<T, Cfg, STEP_JACOBI>, Cfg::NT, smem));
+    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[STEP_Z], k_cg_step<T, Cfg, STEP_Z>, Cfg::NT, smem2));
+    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[STEP_PREC], k_cg_step<T, Cfg, STEP_PREC>, Cfg::NT, smem2));
+    for (int &o : occ3) if (o < 1) o = 1;
     attr_set = true;
   }
-  // chunks of the marching axis: fill whole waves of (SMs x resident CTAs), keep chunks >= 16 planes so the
-  // two extra planes a chunk stages stay cheap
   int nsm = 148;
   MVTV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-  const long long slots = (long long)nsm * occ;
-  int nchunk = 1;
-  double best = -1.0;
-  const int maxchunk = std::max(1, std::min(dt.nz / 16, 256));
-  for (int nc = 1; nc <= maxchunk; ++nc) {
-    const int zc = (dt.nz + nc - 1) / nc;
-    const int ncr = (dt.nz + zc - 1) / zc;
-    const long long total = (long long)tiles * ncr;
-    const long long waves = (total + slots - 1) / slots;
-    const double eff = (double)total / (double)(waves * slots) * ((double)zc / (zc + 2.0));
-    if (eff > best + 1e-9) { best = eff; nchunk = ncr; }
-  }
-  int zchunk = (dt.nz + nchunk - 1) / nchunk;
-  nchunk = (dt.nz + zchunk - 1) / zchunk;
-  const dim3 gs(tiles, (unsigned)nchunk, 1);
+  auto chunking = [&](int occ, int &zchunk_out) {
+    const long long slots = (long long)nsm * occ;
+    int nchunk = 1;
+    double best = -1.0;
+    const int maxchunk = std::max(1, std::min(dt.nz / 16, 256));
+    for (int nc = 1; nc <= maxchunk; ++nc) {
+      const int zc = (dt.nz + nc - 1) / nc;
+      const int ncr = (dt.nz + zc - 1) / zc;
+      const long long total = (long long)tiles * ncr;
+      const long long waves = (total + slots - 1) / slots;
+      const double eff = (double)total / (double)(waves * slots) * ((double)zc / (zc + 2.0));
+      if (eff > best + 1e-9) { best = eff; nchunk = ncr; }
+    }
+    zchunk_out = (dt.nz + nchunk - 1) / nchunk;
+    nchunk = (dt.nz + zchunk_out - 1) / zchunk_out;
+    return dim3(tiles, (unsigned)nchunk, 1);
+  };
+  int zchunk = 1, zchunk_prec = 1;
+  const dim3 gs = chunking(occ3[prec ? STEP_Z : STEP_JACOBI], zchunk);
+  const dim3 gs_prec = chunking(occ3[STEP_PREC], zchunk_prec);
   const int gu = (int)std::max<long long>(1, std::min<long long>(148 * 8, (dt.Nloc + 1023) / 1024));
   int launched = 0;
   int batch = std::max(2, std::min(last_cg_iters, 256));
@@ -852,7 +860,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
         a.seq_red = ++red_seq;
         a.seq_zhalo = ++zhalo_seq;
         prof_begin(MVTV_KC_CG_PREC);
-        k_cg_step<T, Cfg, STEP_PREC><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk);
+        k_cg_step<T, Cfg, STEP_PREC><<<gs_prec, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
         prof_end();
         if (d_peer) {
           k_cg_peer_commit_rz<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
@@ -865,7 +873,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       }
       a.seq_red = ++red_seq;       // a.seq_halo: the version the last producer of r posted
       prof_begin(MVTV_KC_CG_STEP);
-      if (prec) k_cg_step<T, Cfg, STEP_Z><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+      if (prec) k_cg_step<T, Cfg, STEP_Z><<<gs, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       else k_cg_step<T, Cfg, STEP_JACOBI><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       prof_end();
       if (d_peer) {
