@@ -302,10 +302,19 @@ def run_ours(args):
         stages[k] = {"total_ms": ms, "launches": cnt, "performed": performed[k], "avg_ms": avg_ms,
                      "alg_bytes": sb[k], "gbs": sb[k] / (avg_ms * 1e-3) / 1e9, "frac": sb[k] / (avg_ms * 1e-3) / 1e9 / peak}
     dom = max(stages, key=lambda k: stages[k]["total_ms"]) if stages else None
+    # DRAM traffic of the same kernel from the committed ncu --set full capture of this workload (per launch)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_final_ncu_traffic.json")))
+        if world == 1 and args.dtype == "f64" and dom in tr.get(args.workload, {}):
+            traffic = tr[args.workload][dom]["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     roof = None
     if dom:
         roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": stages[dom]["frac"], "traffic": traffic, "alg_bytes_per_launch": stages[dom]["alg_bytes"],
+                "peak_source": peak_src,
                 "share_of_step": stages[dom]["total_ms"] / (dev_s * 1e3)}
     # whole-pass algorithmic bytes: (2R+3N) + 12 N J
     J = inner / max(1, passes)
