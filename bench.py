@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -70,7 +70,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -83,7 +89,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [ln for (ts, ln) in self.lines if t0 - 0.02 <= ts <= t1 + 0.12]   # samples taken DURING the timed region
+        if not inside:
+            inside = [ln for (ts, ln) in self.lines if ts >= t0 - 0.02] or [ln for (_, ln) in self.lines]
+        for ln in inside:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -221,6 +231,8 @@ def run_ours(args):
     n_local = x.shape[0]
 
     # ---- warm-up: operators + W passes ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()            # nvidia-smi needs a moment to come up: start it before the warm-up
     plan.set_points(x, y, axes)
     mode = args.mode
     precond = {"cheb1": mv.PRECOND_CHEB1, "jacobi": mv.PRECOND_JACOBI}[args.precond]
@@ -230,14 +242,14 @@ def run_ours(args):
     warm = mv.WARM_THETA_FROM_PLAN | mv.WARM_U_FROM_PLAN
 
     # ---- timed: exactly K passes, inputs resident in HBM ------------------------------------------
-    sampler = ClockSampler(local_rank)
     if dist:
         dist.barrier()
-    sampler.start()
     plan.profile(True)
+    sampler.begin()
     t0 = time.perf_counter()
     r = plan.solve(args.lam, max_passes=args.steps, flags=warm, rho_init=rw["rho"], rho_matrix0=rw["rho"], **kw)
     wall = time.perf_counter() - t0
+    sampler.end()
     prof = plan.get_profile()
     plan.profile(False)
     clocks = sampler.stop()
@@ -348,7 +360,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
