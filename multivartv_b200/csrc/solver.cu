@@ -673,14 +673,17 @@ template <typename T, typename Cfg, int V>
 void mvtv_plan::launch_zu_march(const ZuArgs<T> &a, const RedBuf &rb) {
   constexpr int Q = Cfg::Q;
   const size_t smem = sizeof(T) * (size_t)Cfg::SMEM_ELEMS;
-  static bool attr_set = false;
-  static int occ = 1;
-  if (!attr_set) {
+  // function attributes are per device: cache them per ordinal (one process may own plans on several GPUs)
+  static bool attr_set_dev[64] = {false};
+  static int occ_dev[64];
+  const int di = device & 63;
+  if (!attr_set_dev[di]) {
     MVTV_CUDA(cudaFuncSetAttribute(k_zu_march<T, Cfg, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_zu_march<T, Cfg, V>, Cfg::NT, smem));
-    if (occ < 1) occ = 1;
-    attr_set = true;
+    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[di], k_zu_march<T, Cfg, V>, Cfg::NT, smem));
+    if (occ_dev[di] < 1) occ_dev[di] = 1;
+    attr_set_dev[di] = true;
   }
+  const int occ = occ_dev[di];
   const int m0 = (int)dt.m[0], m1 = Q >= 2 ? (int)dt.m[1] : 1, m2 = Q >= 3 ? (int)dt.m[2] : 1;
   const long long tiles = (long long)((m0 + Cfg::OX - 1) / Cfg::OX) * ((m1 + Cfg::OY - 1) / Cfg::OY) *
                           ((m2 + Cfg::OW - 1) / Cfg::OW);
@@ -815,17 +818,19 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
                                     ((m2 + Cfg::TW - 1) / Cfg::TW));
   const size_t smem = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_JACOBI>();
   const size_t smem2 = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_Z>();
-  static bool attr_set = false;
-  static int occ3[3] = {1, 1, 1};
-  if (!attr_set) {
+  static bool attr_set_dev[64] = {false};
+  static int occ3_dev[64][3];
+  const int di = device & 63;
+  int *occ3 = occ3_dev[di];
+  if (!attr_set_dev[di]) {
     MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_JACOBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[STEP_JACOBI], k_cg_step<T, Cfg, STEP_JACOBI>, Cfg::NT, smem));
     MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[STEP_Z], k_cg_step<T, Cfg, STEP_Z>, Cfg::NT, smem2));
     MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[STEP_PREC], k_cg_step<T, Cfg, STEP_PREC>, Cfg::NT, smem2));
-    for (int &o : occ3) if (o < 1) o = 1;
-    attr_set = true;
+    for (int k = 0; k < 3; ++k) if (occ3[k] < 1) occ3[k] = 1;
+    attr_set_dev[di] = true;
   }
   int nsm = 148;
   MVTV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));

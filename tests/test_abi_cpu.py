@@ -100,3 +100,23 @@ def test_host_mesh_helpers_match_reference_semantics():
     assert all(np.array_equal(a, b) for a, b in zip(ax, back))
     d = mv.create_deltas(x, [4, 5], "cpp")
     assert np.allclose(d, (x.max(0) - x.min(0) + 0.02) / np.array([4, 5]))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) prints one JSON line with the contract's
+    keys; it runs the oracle port on the bounded 1024^2 sample, no GPU involved."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "mesh_vertex_updates_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["vs_baseline"] is None and d["config"]["workload"].startswith("2-D 4096x4096")
