@@ -487,3 +487,24 @@ def test_cheb1_midsize_and_fp32(mv):
         pl.set_points(xx, yy, axes)
         out = pl.solve(1.0, mode="rcpp", max_passes=30, precond=mv.PRECOND_CHEB1)
     assert np.abs(out["theta"] - ref["theta"]).max() <= FP32_TOL
+
+
+def test_gather_kernel_cross_check(mv, monkeypatch):
+    """k_zu (gather form, the simple first version) and k_zu_march (scatter form, the fast one) are two independent
+    implementations of the same fused z/u update: same Counter, theta within 1e-12, on 2-D / 3-D / 4-D meshes."""
+    for dims, n in ([40, 37], 3000), ([11, 11, 12], 3000), ([6, 6, 6, 7], 3000):
+        p = len(dims)
+        x, y = synth(70 + p, n, p, 0.0, 1.0, 0.5)
+        axes = po.mesh_axes(x, dims, po.MODE_RCPP)
+        monkeypatch.delenv("MVTV_ZU_KERNEL", raising=False)
+        with mv.Plan(dims) as pl:
+            pl.set_points(x, y, axes)
+            a = pl.solve(0.8, mode="rcpp", want_u=True)
+        monkeypatch.setenv("MVTV_ZU_KERNEL", "gather")
+        with mv.Plan(dims) as pl:
+            pl.set_points(x, y, axes)
+            b = pl.solve(0.8, mode="rcpp", want_u=True)
+        monkeypatch.delenv("MVTV_ZU_KERNEL", raising=False)
+        assert a["counter"] == b["counter"]
+        assert np.abs(a["theta"] - b["theta"]).max() <= 1e-12
+        assert np.abs(a["u"] - b["u"]).max() <= 1e-11
