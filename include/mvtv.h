@@ -119,6 +119,11 @@ int mvtv_device_count(int *count);
 /* 128-byte ncclUniqueId for mvtv_plan_desc.nccl_unique_id: call on one rank, broadcast to the others
  * (e.g. with torch.distributed), then every rank creates its plan. */
 int mvtv_nccl_unique_id(void *out128);
+/* Page-locked (pinned) host buffers.  Not a reference function: the reference never leaves host memory.  Every
+ * host pointer of this ABI may be pageable; when it was obtained here, the cudaMemcpyAsync behind the call is a
+ * direct DMA transfer at PCIe speed instead of a staged copy (points in, theta / fitted / u out). */
+int mvtv_host_alloc(void **out, uint64_t bytes);
+int mvtv_host_free(void *ptr);
 
 /* -- plan = operators of create_cache_objects (cpp-code/solvers.cpp:31-41) kept on the device ----- */
 /* Replaces: create_D (cpp-code/utils.cpp:245-269) -- D is never materialised, only its block table. */
@@ -197,6 +202,11 @@ int mvtv_apply_Dt(mvtv_plan *plan, const double *rows, double *out_vertices);
 int mvtv_apply_M(mvtv_plan *plan, double s, const double *x, double *out);
 /* Replaces: softthresh (cpp-code/solvers.hpp:22) */
 int mvtv_softthresh(int64_t n, const double *z, double lam, double *out);
+/* Replaces: adapt_step (cpp-code/solvers.hpp:77-82, solvers.cpp:70-88 for MVTV_MODE_CPP: r > 20 s -> rho x20, u x0.05;
+ * s > 20 r -> rho x0.1, u x10 ; rcpp solvers.cpp:77-94 for MVTV_MODE_RCPP: factor 10, tau = 2).  r: primal residual
+ * (n_r), s: dual residual (n_s), u (n_u, may be 0).  rho_next is NOT truncated to int (the caller does, cpp :126). */
+int mvtv_adapt_step(int mode, int64_t n_r, const double *r, int64_t n_s, const double *s, double rho, int64_t n_u,
+                    const double *u, double *rho_next, double *u_next);
 /* Replaces: nearest1 (cpp-code/utils.hpp:70) on a tensor-product mesh */
 int mvtv_nearest(int p, const int64_t *m, const double *axes, int64_t n, const double *data_colmajor,
                  int64_t *vertex_out);

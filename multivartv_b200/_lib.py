@@ -23,9 +23,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmvtv_b200.so")
 
 SYMBOLS = [
-    "mvtv_abi_version", "mvtv_last_error", "mvtv_device_count", "mvtv_nccl_unique_id", "mvtv_plan_create", "mvtv_plan_destroy",
+    "mvtv_abi_version", "mvtv_last_error", "mvtv_device_count", "mvtv_nccl_unique_id", "mvtv_host_alloc", "mvtv_host_free", "mvtv_plan_create", "mvtv_plan_destroy",
     "mvtv_plan_info", "mvtv_plan_profile", "mvtv_plan_get_profile", "mvtv_plan_set_points", "mvtv_plan_set_points_strided", "mvtv_plan_set_points_dev", "mvtv_plan_get_cache", "mvtv_solve", "mvtv_solve_path", "mvtv_lambda_max",
-    "mvtv_predict", "mvtv_apply_D", "mvtv_apply_Dt", "mvtv_apply_M", "mvtv_softthresh", "mvtv_nearest",
+    "mvtv_predict", "mvtv_apply_D", "mvtv_apply_Dt", "mvtv_apply_M", "mvtv_softthresh", "mvtv_adapt_step", "mvtv_nearest",
 ]
 
 
@@ -77,6 +77,8 @@ def load():
     L.mvtv_last_error.restype = C.c_char_p
     L.mvtv_device_count.argtypes = [C.POINTER(C.c_int)]
     L.mvtv_nccl_unique_id.argtypes = [vp]
+    L.mvtv_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
+    L.mvtv_host_free.argtypes = [vp]
     L.mvtv_plan_create.argtypes = [C.POINTER(vp), C.POINTER(PlanDesc)]
     L.mvtv_plan_destroy.argtypes = [vp]
     L.mvtv_plan_info.argtypes = [vp, ip, ip, ip, ip]
@@ -95,6 +97,7 @@ def load():
     L.mvtv_apply_Dt.argtypes = [vp, dp, dp]
     L.mvtv_apply_M.argtypes = [vp, C.c_double, dp, dp]
     L.mvtv_softthresh.argtypes = [C.c_int64, dp, C.c_double, dp]
+    L.mvtv_adapt_step.argtypes = [C.c_int, C.c_int64, dp, C.c_int64, dp, C.c_double, C.c_int64, dp, dp, dp]
     L.mvtv_nearest.argtypes = [C.c_int, ip, dp, C.c_int64, dp, ip]
     for name in SYMBOLS:
         fn = getattr(L, name)

@@ -1232,6 +1232,23 @@ int mvtv_nccl_unique_id(void *out128) {
   });
 }
 
+int mvtv_host_alloc(void **out, uint64_t bytes) {
+  return guarded([&] {
+    MVTV_REQUIRE(out, "null argument");
+    *out = nullptr;
+    MVTV_REQUIRE(bytes > 0, "bytes must be > 0");
+    MVTV_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    return MVTV_OK;
+  });
+}
+
+int mvtv_host_free(void *ptr) {
+  return guarded([&] {
+    if (ptr) MVTV_CUDA(cudaFreeHost(ptr));
+    return MVTV_OK;
+  });
+}
+
 int mvtv_plan_create(mvtv_plan **out, const mvtv_plan_desc *d) {
   return guarded([&] {
     MVTV_REQUIRE(out && d, "null argument");
@@ -1641,6 +1658,57 @@ int mvtv_softthresh(int64_t n, const double *z, double lam, double *out) {
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(out, buf + n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    MVTV_CUDA(e);
+    return (int)MVTV_OK;
+  });
+}
+
+// adapt_step (cpp-code/solvers.cpp:70-88 ; rcpp solvers.cpp:77-94) as a stand-alone call: ||r||, ||s|| by the
+// deterministic grid reduction, then the rescale of u.  The ADMM loop itself never calls this: there the norms come
+// out of k_zu_march and the rescale is the lazy `uscale`.
+int mvtv_adapt_step(int mode, int64_t n_r, const double *r, int64_t n_s, const double *s_vec, double rho, int64_t n_u,
+                    const double *u, double *rho_next, double *u_next) {
+  return guarded([&] {
+    MVTV_REQUIRE(mode == MVTV_MODE_CPP || mode == MVTV_MODE_RCPP, "mode must be MVTV_MODE_CPP or MVTV_MODE_RCPP");
+    MVTV_REQUIRE(n_r >= 1 && n_s >= 1 && n_u >= 0 && r && s_vec && rho_next && (n_u == 0 || (u && u_next)), "bad argument");
+    const int g = mvtv_plan::grid1d(std::max(n_r, n_s));
+    const size_t words = (size_t)n_r + (size_t)n_s + (size_t)n_u + (size_t)g + 4;
+    double *buf = nullptr;
+    MVTV_CUDA(cudaMalloc(&buf, sizeof(double) * words));
+    double *d_r = buf, *d_s = buf + n_r, *d_u = d_s + n_s, *d_part = d_u + n_u, *d_out = d_part + g;
+    unsigned *d_cnt = (unsigned *)(d_out + 2);
+    double h[2] = {0.0, 0.0};
+    cudaError_t e = cudaMemset(d_out, 0, sizeof(double) * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_r, r, sizeof(double) * (size_t)n_r, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_s, s_vec, sizeof(double) * (size_t)n_s, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_u) e = cudaMemcpy(d_u, u, sizeof(double) * (size_t)n_u, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      k_dot<double><<<mvtv_plan::grid1d(n_r), 256>>>(d_r, d_r, 0, n_r, RedBuf{d_part, d_cnt}, d_out);
+      k_dot<double><<<mvtv_plan::grid1d(n_s), 256>>>(d_s, d_s, 0, n_s, RedBuf{d_part, d_cnt}, d_out + 1);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(h, d_out, sizeof(double) * 2, cudaMemcpyDeviceToHost);
+    double factor = 1.0;
+    if (e == cudaSuccess) {
+      const double r_norm = sqrt(h[0]), s_norm = sqrt(h[1]);
+      const double thr = (mode == MVTV_MODE_CPP) ? 20.0 : 10.0;
+      *rho_next = rho;
+      if (r_norm > thr * s_norm) {          // cpp :75-79 (x20, x0.05) ; rcpp :82-85 (x2, x1/2)
+        *rho_next = (mode == MVTV_MODE_CPP) ? 20 * rho : 2.0 * rho;
+        factor = (mode == MVTV_MODE_CPP) ? 0.05 : 1.0 / 2.0;
+      } else if (s_norm > thr * r_norm) {   // cpp :80-83 (x0.1, x10) ; rcpp :86-89 (x1/2, x2)
+        *rho_next = (mode == MVTV_MODE_CPP) ? 0.1 * rho : 1.0 / 2.0 * rho;
+        factor = (mode == MVTV_MODE_CPP) ? 10.0 : 2.0;
+      }
+      if (n_u) {
+        if (factor != 1.0) {
+          k_scale<double><<<mvtv_plan::grid1d(n_u), 256>>>(d_u, n_u, factor);
+          e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(u_next, d_u, sizeof(double) * (size_t)n_u, cudaMemcpyDeviceToHost);
+      }
+    }
     cudaFree(buf);
     MVTV_CUDA(e);
     return (int)MVTV_OK;

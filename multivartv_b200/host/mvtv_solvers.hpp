@@ -7,6 +7,10 @@
 //   admm_update       cpp-code/solvers.hpp:85          (rcpp: solvers.hpp:100, in namespace mvtv::rcpp)
 //   mbs_one           cpp-code/solvers.hpp:89          (rcpp: solvers.hpp:104)
 //   mbs_predict, mse, mbs_mse   cpp-code/solvers.hpp:93-97
+//   adapt_step        cpp-code/solvers.hpp:77-82       (rcpp: solvers.hpp:80-85, in namespace mvtv::rcpp)
+//   create_lambdas, mbs_path, test_mse, mbs_fit_optimal, gen_mesh, gen_ftrue, mbs   cpp-code/solvers.hpp:101-129
+//   kfold, kfoldinds, rowmean   cpp-code/utils.cpp:406-436 ; rcpp utils.cpp:357-376
+//   rcpp::mbs_impl    rcpp-code/MultivarTV/src/solvers.cpp:305-376 (the Rcpp::List as a struct)
 //   create_mesh, create_deltas, nearest1   cpp-code/utils.hpp:59-70
 //
 // Upstream passes Armadillo types by value; Armadillo is not a dependency here: `mvtv::vec` / `mvtv::mat`
@@ -16,6 +20,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <limits>
@@ -215,6 +220,14 @@ inline void create_cache_objects(const mat &data, const vec &y, const MAT &mesh,
   check(mvtv_plan_set_points(inits.plan, inits.n, data.memptr(), y.memptr(), inits.axes.data()));
 }
 
+// Re-bin a new point set on the operators already held by `inits` (the per-fold create_cache_objects +
+// fill_cache of rcpp solvers.cpp:347-348 without rebuilding the plan: D depends only on m and deltas)
+inline void cache_set_points(mbs_cache &inits, const mat &data, const vec &y) {
+  if (!inits.plan) throw std::logic_error("cache_set_points: empty cache");
+  inits.n = (int64_t)data.n_rows;
+  check(mvtv_plan_set_points(inits.plan, inits.n, data.memptr(), y.memptr(), inits.axes.data()));
+}
+
 inline mvtv_solve_params default_params(int mode, double lambda) {
   mvtv_solve_params p{};
   p.struct_size = (int32_t)sizeof(p);
@@ -290,17 +303,19 @@ typedef struct mbs_object {  // cpp-code/solvers.hpp:56-62
   double minmse = 0.0;
   double minmse_lambda = 0.0;
   vec mses;
+  vec rhos;  // final rho of every solve of the path (RCPP mode carries it to the next lambda, rcpp solvers.cpp:218)
 } mbs_object;
 
 // lam_max_pinv (cpp-code/utils.cpp:399-404) on the cached operators, then the grid of create_lambdas
 // (cpp-code/solvers.cpp:179-192): flipud(exp(linspace(log(1e-5*lambda_max), log(lambda_max), n_lambda)))
-inline vec create_lambdas(int n_lambda, mbs_cache &inits, vec *lambdas = NULL) {
+// (rcpp solvers.cpp:186-200: CGNR lambda_max, grid from 1e-4*lambda_max)
+inline vec create_lambdas(int n_lambda, mbs_cache &inits, vec *lambdas = NULL, int mode = MVTV_MODE_CPP) {
   if (lambdas != NULL) return *lambdas;
   double lambda_max = 0.0;
-  check(mvtv_lambda_max(inits.plan, MVTV_MODE_CPP, &lambda_max, nullptr));
+  check(mvtv_lambda_max(inits.plan, mode, &lambda_max, nullptr));
   std::printf("lambda_max = %f ", lambda_max);
   vec out((size_t)n_lambda);
-  const double a = std::log(lambda_max * 0.00001), b = std::log(lambda_max);
+  const double a = std::log(lambda_max * (mode == MVTV_MODE_RCPP ? 0.0001 : 0.00001)), b = std::log(lambda_max);
   for (int i = 0; i < n_lambda; ++i) {
     const double t = (n_lambda == 1 || i == n_lambda - 1) ? b : a + double(i) * ((b - a) / double(n_lambda - 1));
     out[(size_t)(n_lambda - 1 - i)] = std::exp(t);
@@ -317,9 +332,10 @@ inline void mbs_path(const mat &data, const vec &y, const vec &m, const MAT &mes
   std::vector<double> thetas((size_t)n_lambda * N);
   std::vector<int32_t> counters((size_t)n_lambda);
   vec MSEs((size_t)n_lambda);
+  output.rhos = vec((size_t)n_lambda);
   int32_t best = 0;
   check(mvtv_solve_path(inits.plan, &p, n_lambda, lambdas.memptr(), ftrue.memptr(), MSEs.memptr(), counters.data(),
-                        nullptr, thetas.data(), nullptr, nullptr, &best, &total));
+                        output.rhos.memptr(), thetas.data(), nullptr, nullptr, &best, &total));
   for (int i = 0; i < n_lambda; ++i) {
     std::printf("Lambda = %f, Counter = %i \n", lambdas[(size_t)i], counters[(size_t)i]);
     mbs_one_object model;
@@ -339,6 +355,222 @@ inline void mbs_path(const mat &data, const vec &y, const vec &m, const MAT &mes
   output.minmse = MSEs[(size_t)best];
   output.minmse_lambda = lambdas[(size_t)best];
   output.mses = MSEs;
+}
+
+// ---- adapt_step (cpp-code/solvers.hpp:77-82) ---------------------------------------------------------------
+typedef struct adaptstep {
+  double rho_next = 0.0;
+  vec u_next;
+} adaptstep;
+
+inline void adapt_step_mode(int mode, const vec &r_current, const vec &s_current, double rho_current, const vec &u_current,
+                            adaptstep &object) {
+  object.u_next = vec(u_current.size());
+  check(mvtv_adapt_step(mode, (int64_t)r_current.size(), r_current.memptr(), (int64_t)s_current.size(), s_current.memptr(),
+                        rho_current, (int64_t)u_current.size(), u_current.memptr(), &object.rho_next, object.u_next.memptr()));
+}
+inline void adapt_step(const vec &r_current, const vec &s_current, double rho_current, const vec &u_current,
+                       adaptstep &object) {  // cpp-code/solvers.cpp:70-88
+  adapt_step_mode(MVTV_MODE_CPP, r_current, s_current, rho_current, u_current, object);
+}
+
+// ---- cross-validation helpers (cpp-code/utils.cpp:406-436 ; rcpp utils.cpp:357-376) -------------------------
+inline vec rowmean(const mat &A) {  // cpp-code/utils.cpp:406-413
+  vec r(A.n_rows);
+  for (size_t i = 0; i < A.n_rows; ++i) {
+    double sacc = 0.0;
+    for (size_t j = 0; j < A.n_cols; ++j) sacc += A(i, j);
+    r[i] = sacc / double(A.n_cols);
+  }
+  return r;
+}
+
+inline mat take_rows(const mat &A, const std::vector<size_t> &ids) {
+  mat out(ids.size(), A.n_cols);
+  for (size_t j = 0; j < A.n_cols; ++j)
+    for (size_t i = 0; i < ids.size(); ++i) out(i, j) = A(ids[i], j);
+  return out;
+}
+inline vec take_rows(const vec &a, const std::vector<size_t> &ids) {
+  vec out(ids.size());
+  for (size_t i = 0; i < ids.size(); ++i) out[i] = a[ids[i]];
+  return out;
+}
+
+// arma::shuffle's RNG stream is not reproducible outside Armadillo: a seeded Fisher-Yates on splitmix64 instead
+inline uint64_t splitmix64(uint64_t &state) {
+  uint64_t z = (state += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+template <typename V>
+inline void seeded_shuffle(V &v, uint64_t seed) {
+  uint64_t st = seed;
+  for (size_t i = v.size(); i > 1; --i) std::swap(v[i - 1], v[(size_t)(splitmix64(st) % (uint64_t)i)]);
+}
+
+// kfoldinds (rcpp utils.cpp:367-376): fold label i % k per row, shuffled
+inline std::vector<int> kfoldinds(int n, int k, uint64_t seed = 117) {
+  std::vector<int> idx((size_t)n);
+  for (int i = 0; i < n; ++i) idx[(size_t)i] = i % k;
+  seeded_shuffle(idx, seed);
+  return idx;
+}
+
+// kfold (cpp-code/utils.cpp:417-436): rows shuffled once, fold i tests on the i-th block of n/k rows
+typedef struct kfolds {
+  std::vector<mat> Xtrain, Xtest;
+  std::vector<vec> Ytrain, Ytest;
+} kfolds;
+inline void kfold(int k, const mat &data, const vec &y, kfolds &struck, uint64_t seed = 117) {
+  const size_t n = data.n_rows, ntest = n / (size_t)k;
+  std::vector<size_t> perm(n);
+  for (size_t i = 0; i < n; ++i) perm[i] = i;
+  seeded_shuffle(perm, seed);
+  for (int i = 0; i < k; ++i) {
+    const size_t first = (size_t)i * ntest, last = (size_t)(i + 1) * ntest;
+    std::vector<size_t> te(perm.begin() + (long)first, perm.begin() + (long)last), tr(perm.begin(), perm.begin() + (long)first);
+    tr.insert(tr.end(), perm.begin() + (long)last, perm.end());
+    struck.Xtest.push_back(take_rows(data, te));
+    struck.Ytest.push_back(take_rows(y, te));
+    struck.Xtrain.push_back(take_rows(data, tr));
+    struck.Ytrain.push_back(take_rows(y, tr));
+  }
+}
+
+inline MAT gen_mesh(const mat &data, const vec &m, MAT *mesh, bool rcpp = false) {  // cpp-code/solvers.cpp:221-231
+  if (mesh != NULL) return *mesh;
+  return mesh_from_axes(mesh_axes(data, m, rcpp));
+}
+inline vec gen_ftrue(const vec &y, vec *ftrue) { return ftrue == NULL ? y : *ftrue; }  // cpp-code/solvers.cpp:235-244
+
+// test_mse (cpp-code/solvers.cpp:264-273): predict the held-out points with every model of the path
+inline vec test_mse(const mat &data, const vec &y, const mbs_object &path_object, int n_lambda) {
+  vec mses((size_t)n_lambda);
+  if (n_lambda == 0) return mses;
+  const std::vector<long long> idx = nearest1(data, path_object.models[0].mesh, path_object.models[0].m);
+  for (int i = 0; i < n_lambda; ++i) {  // O*theta for a one-hot O is a gather at the nearest vertices
+    const vec &th = path_object.models[(size_t)i].theta_hat;
+    double sacc = 0.0;
+    for (size_t j = 0; j < idx.size(); ++j) sacc += (th[(size_t)idx[j]] - y[j]) * (th[(size_t)idx[j]] - y[j]);
+    mses[(size_t)i] = sacc / double(y.size());
+  }
+  return mses;
+}
+
+inline size_t index_min(const vec &v) {  // first minimum, like arma's index_min / find(v - min(v) == 0)[0]
+  size_t b = 0;
+  for (size_t i = 1; i < v.size(); ++i)
+    if (v[i] < v[b]) b = i;
+  return b;
+}
+
+// mbs_fit_optimal (cpp-code/solvers.cpp:248-260 ; rcpp solvers.cpp:261-274): refit at the lambda with the lowest mean MSE.
+// The cached system matrix is whatever the last solve of mbs_path left behind (cpp: crossO + lambdas[last]*crossD,
+// warm start from the path's theta; rcpp: cold start, rho = lambdas[0]/5, matrix scalar = the rho the path's
+// second-to-last solve ended with).
+inline void mbs_fit_optimal(const mat &data, const vec &y, const vec &m, mbs_one_object &best_model, const MAT &mesh,
+                            const vec &lambdas, const mat &mse_mat, mbs_cache &cache, const mbs_object &path_object,
+                            int mode = MVTV_MODE_CPP) {
+  const vec mean_mses = rowmean(mse_mat);
+  const size_t best = index_min(mean_mses), nl = lambdas.size();
+  mvtv_solve_params p = default_params(mode, lambdas[best]);
+  mvtv_solve_result r{};
+  best_model.theta_hat = vec((size_t)cache.ntheta);
+  best_model.fitted = vec((size_t)cache.n);
+  int code;
+  if (mode == MVTV_MODE_RCPP) {
+    p.rho_init = lambdas[0] / 5.0;
+    p.rho_matrix0 = (nl >= 2 && path_object.rhos.size() == nl) ? path_object.rhos[nl - 2] : lambdas[0] / 5.0;
+    code = mvtv_solve(cache.plan, &p, nullptr, nullptr, best_model.theta_hat.memptr(), best_model.fitted.memptr(), &r);
+    if (code == MVTV_ERR_NOT_CONVERGED) code = MVTV_OK;  // rcpp solvers.cpp:129-132: message + break
+  } else {
+    p.rho_matrix0 = lambdas[nl - 1];
+    code = mvtv_solve(cache.plan, &p, path_object.models[best].theta_hat.memptr(), nullptr, best_model.theta_hat.memptr(),
+                      best_model.fitted.memptr(), &r);
+  }
+  check(code);
+  std::printf("Lambda = %f, Counter = %i \n", lambdas[best], r.counter);
+  best_model.mesh = mesh;
+  best_model.data = data;
+  best_model.y = y;
+  best_model.m = m;
+  best_model.rhohat = r.rho;
+  best_model.counter = r.counter;
+}
+
+// What rcpp's mbs_impl hands back to R (Rcpp::List, rcpp solvers.cpp:368-373), as a struct
+typedef struct mbs_cv_object {
+  mbs_one_object best_model;  // data, fitted, m, mesh, theta_hat, y
+  vec residuals;              // y - fitted
+  MBSVEC models;              // the final path on the full data; models[i].theta_hat / fitted
+  vec lambdas, path_mses;     // lambda and mse of every model of the final path
+  int lambda_minmse_ind = 0;  // 1-based, like the R list
+  vec cv_mses;                // "cv.mses": mean MSE over the folds per lambda
+  mat mse_mat;                // n_lambda x folds
+} mbs_cv_object;
+
+// The model-selection driver behind mbs (cpp-code/solvers.cpp:277-310) and mbs_impl (rcpp solvers.cpp:305-376).
+// Data flow follows rcpp-code, which repairs cpp-code's CV (there every fold re-used the full-data operators and
+// path_object.models was never cleared): per-fold operators, a fresh path per fold, final path on the full data.
+// `mode` selects the ADMM loop and the mesh / delta / lambda-grid conventions of that sibling.  `foldinds` (length n,
+// values 0..folds-1) overrides the seeded shuffle.
+inline void mbs_cv(const mat &data, const vec &y, const vec &m, mbs_cv_object &out, MAT *mesh, int n_lambda, vec *ftrue,
+                   vec *lambdas, int folds, int mode, bool verbose = true, const std::vector<int> *foldinds = nullptr,
+                   uint64_t seed = 117) {
+  const bool rc = (mode == MVTV_MODE_RCPP);
+  const vec deltas = create_deltas(data, m, rc ? 0.0001 : 0.01);  // inits.deltas (cpp :281 / rcpp :310)
+  const MAT MESH = gen_mesh(data, m, mesh, rc);
+  if (verbose) std::printf("MBS BEGINS: ntheta = %i \n", (int)prodd(m));
+  mbs_cache cache;
+  create_cache_objects(data, y, MESH, m, cache, deltas);  // + fill_cache
+  const vec LAMBDAS = create_lambdas(n_lambda, cache, lambdas, mode);
+  n_lambda = (int)LAMBDAS.size();
+  const vec FTRUE = gen_ftrue(y, ftrue);
+  mbs_object final_path;
+  const int ncol = folds < 1 ? 1 : folds;
+  out.mse_mat = mat((size_t)n_lambda, (size_t)ncol);
+  if (folds <= 1) {
+    mbs_path(data, y, m, MESH, n_lambda, LAMBDAS, FTRUE, final_path, cache, mode);
+    for (int i = 0; i < n_lambda; ++i) out.mse_mat((size_t)i, 0) = mse(final_path.models[(size_t)i].fitted, y);  // test_mse on the training data (rcpp :330)
+    mbs_fit_optimal(data, y, m, out.best_model, MESH, LAMBDAS, out.mse_mat, cache, final_path, mode);
+    out.cv_mses = rowmean(out.mse_mat);
+  } else {
+    std::vector<int> labels = foldinds ? *foldinds : kfoldinds((int)data.n_rows, folds, seed);
+    if (labels.size() != data.n_rows) throw std::invalid_argument("mbs: foldinds must have one label per row of data");
+    for (int f = 0; f < folds; ++f) {
+      std::vector<size_t> tr, te;
+      for (size_t i = 0; i < labels.size(); ++i) (labels[i] == f ? te : tr).push_back(i);
+      if (te.empty() || tr.empty()) throw std::invalid_argument("mbs: empty fold");
+      const mat train_x = take_rows(data, tr), test_x = take_rows(data, te);
+      const vec train_y = take_rows(y, tr), test_y = take_rows(y, te);
+      cache_set_points(cache, train_x, train_y);  // per-fold operators (rcpp :347-348)
+      mbs_object path_object;
+      mbs_path(train_x, train_y, m, MESH, n_lambda, LAMBDAS, train_y, path_object, cache, mode);
+      if (verbose) std::printf("Fold = %i Done \n", f + 1);
+      const vec col = test_mse(test_x, test_y, path_object, n_lambda);
+      for (int i = 0; i < n_lambda; ++i) out.mse_mat((size_t)i, (size_t)f) = col[(size_t)i];
+    }
+    cache_set_points(cache, data, y);  // final path on the full data (rcpp :355-358)
+    mbs_path(data, y, m, MESH, n_lambda, LAMBDAS, y, final_path, cache, mode);
+    out.cv_mses = rowmean(out.mse_mat);
+    out.best_model = final_path.models[index_min(out.cv_mses)];
+  }
+  out.lambda_minmse_ind = (int)index_min(out.cv_mses) + 1;
+  out.models = final_path.models;
+  out.lambdas = LAMBDAS;
+  out.path_mses = final_path.mses;
+  out.residuals = vec(y.size());
+  for (size_t i = 0; i < y.size(); ++i) out.residuals[i] = y[i] - out.best_model.fitted[i];
+}
+
+// mbs (cpp-code/solvers.hpp:129): cross-validated fit, best model returned through `output`
+inline void mbs(const mat &data, const vec &y, const vec &m, mbs_one_object &output, MAT *mesh = NULL, int n_lambda = 100,
+                vec *ftrue = NULL, vec *lambdas = NULL, int folds = 5) {
+  mbs_cv_object cv;
+  mbs_cv(data, y, m, cv, mesh, n_lambda, ftrue, lambdas, folds, MVTV_MODE_CPP);
+  output = cv.best_model;
 }
 
 // ---- rcpp-code/MultivarTV/src/solvers.hpp variants ---------------------------------------------------
@@ -394,6 +626,20 @@ inline void mbs_one(const mat &data, const vec &y, const vec &m, mbs_one_object 
   output.y = y;
   output.m = m;
   output.counter = counter;
+}
+
+inline void adapt_step(const vec &r_current, const vec &s_current, double rho_current, const vec &u_current,
+                       adaptstep &object) {  // rcpp solvers.cpp:77-94
+  adapt_step_mode(MVTV_MODE_RCPP, r_current, s_current, rho_current, u_current, object);
+}
+
+// mbs_impl (rcpp solvers.cpp:305-376): what R's mvtv() receives, as a struct
+inline mbs_cv_object mbs_impl(const mat &data, const vec &y, const vec &m, MAT *mesh = NULL, int n_lambda = 100,
+                              vec *ftrue = NULL, vec *lambdas = NULL, int folds = 5, bool verbose = true,
+                              const std::vector<int> *foldinds = nullptr) {
+  mbs_cv_object cv;
+  mbs_cv(data, y, m, cv, mesh, n_lambda, ftrue, lambdas, folds, MVTV_MODE_RCPP, verbose, foldinds);
+  return cv;
 }
 }  // namespace rcpp
 

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 
 import numpy as np
 
@@ -132,6 +133,39 @@ def softthresh(z, lam):
     return out
 
 
+def adapt_step(r, s, rho, u, mode="cpp"):
+    """cpp-code/solvers.hpp:77-82 (solvers.cpp:70-88) / rcpp solvers.cpp:77-94: returns (rho_next, u_next)."""
+    r, s, u = _f64(np.asarray(r).ravel()), _f64(np.asarray(s).ravel()), _f64(np.asarray(u).ravel())
+    u_next = np.empty_like(u)
+    rho_next = C.c_double(0.0)
+    _lib.check(_lib.load().mvtv_adapt_step(_MODES[mode], r.size, _dp(r), s.size, _dp(s), float(rho), u.size, _dp(u),
+                                           C.byref(rho_next), _dp(u_next)))
+    return rho_next.value, u_next
+
+
+def pinned_empty(shape, dtype=np.float64, order="C"):
+    """numpy array in page-locked host memory (mvtv_host_alloc): host<->device copies of arrays allocated here
+    run as direct DMA transfers.  The memory is released when the last view of the array dies."""
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(v) for v in shape)
+    dt = np.dtype(dtype)
+    nbytes = max(1, int(np.prod(shape)) * dt.itemsize)
+    L = _lib.load()
+    ptr = C.c_void_p()
+    _lib.check(L.mvtv_host_alloc(C.byref(ptr), nbytes))
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    weakref.finalize(buf, L.mvtv_host_free, ptr.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape)))
+    return arr.reshape(shape, order=order)
+
+
+def _out_buffer(out, size, name):
+    """Caller-provided output array (e.g. from pinned_empty): must be contiguous float64 of the right size."""
+    if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.size == size
+            and out.flags.writeable):
+        raise ValueError("%s must be a writeable C-contiguous float64 array of %d elements" % (name, size))
+    return out
+
+
 def nccl_unique_id() -> bytes:
     """128-byte ncclUniqueId (generate on rank 0, broadcast, pass to every rank's Plan)."""
     buf = C.create_string_buffer(128)
@@ -231,7 +265,10 @@ class Plan:
     # -- the hot path ------------------------------------------------------------------------
     def solve(self, lam, mode="cpp", theta_init=None, u_init=None, rho_init=None, rho_matrix0=None, tol=None,
               max_counter=0, max_passes=0, cg_rtol=0.0, cg_maxit=0, precond=PRECOND_AUTO, flags=0,
-              want_u=False, want_fitted=True, want_theta=True, raise_on_nonconvergence=True):
+              want_u=False, want_fitted=True, want_theta=True, raise_on_nonconvergence=True, theta_out=None,
+              fitted_out=None):
+        """admm_update + fitted (mvtv_solve).  ``theta_out`` / ``fitted_out``: optional preallocated float64 arrays
+        (``pinned_empty``) that receive the outputs instead of fresh numpy arrays."""
         L = _lib.load()
         mode = _MODES[mode]
         prm = _lib.SolveParams()
@@ -254,8 +291,10 @@ class Plan:
                 u = np.zeros(self.R)
             else:
                 u = np.empty(self.R)  # CPP/PY ignore the input, only the output is used
-        theta = np.empty(self.n_local) if want_theta else None
-        fitted = np.empty(self.n) if want_fitted else None
+        theta = (_out_buffer(theta_out, self.n_local, "theta_out") if theta_out is not None
+                 else np.empty(self.n_local)) if want_theta else None
+        fitted = (_out_buffer(fitted_out, self.n, "fitted_out") if fitted_out is not None
+                  else np.empty(self.n)) if want_fitted else None
         res = _lib.SolveResult()
         allow = () if raise_on_nonconvergence else (_lib.ERR_NOT_CONVERGED,)
         if mode == MODE_RCPP:
