@@ -12,6 +12,7 @@
 //   kfold, kfoldinds, rowmean   cpp-code/utils.cpp:406-436 ; rcpp utils.cpp:357-376
 //   rcpp::mbs_impl    rcpp-code/MultivarTV/src/solvers.cpp:305-376 (the Rcpp::List as a struct)
 //   create_mesh, create_deltas, nearest1   cpp-code/utils.hpp:59-70
+//   prod, range, tensor2vector, vector2tensor, dec2binary, fd_binaries   cpp-code/utils.hpp:17-37 (host index maps)
 //
 // Upstream passes Armadillo types by value; Armadillo is not a dependency here: `mvtv::vec` / `mvtv::mat`
 // are minimal column-major containers with the few members the interface needs (n_rows, n_cols, memptr(),
@@ -85,6 +86,46 @@ inline void check(int code) {
 }
 
 // ---- utils.hpp -------------------------------------------------------------------------------------
+typedef std::vector<int> VEC;  // cpp-code/utils.hpp:11
+
+inline int prod(int p, const VEC &v) {  // cpp-code/utils.cpp:14-22
+  int out = 1;
+  for (int i = 0; i < p; ++i) out *= v[(size_t)i];
+  return out;
+}
+inline VEC range(int lo, int hi) {  // cpp-code/utils.cpp:32-38
+  VEC v((size_t)(hi - lo + 1));
+  for (int i = 0; i < hi - lo + 1; ++i) v[(size_t)i] = lo + i;
+  return v;
+}
+// column-major flattening, axis 0 fastest (cpp-code/utils.cpp:40-52)
+inline int tensor2vector(int p, const VEC &multi_ind, const VEC &dims) {
+  int v = multi_ind[0];
+  for (int i = 1; i < p; ++i) v += multi_ind[(size_t)i] * prod(i, dims);
+  return v;
+}
+// cpp-code/utils.cpp:54-71; upstream divides in float (exact for N <= 2^24), integer ceil here
+inline VEC vector2tensor(int p, int vec_ind, const VEC &dims) {
+  VEC out((size_t)p);
+  int ind2 = vec_ind + 1;
+  for (int i = p; i > 0; --i) {
+    const int dp = prod(i - 1, dims);
+    out[(size_t)(i - 1)] = std::max(1, (ind2 + dp - 1) / dp) - 1;
+    ind2 -= out[(size_t)(i - 1)] * dp;
+  }
+  return out;
+}
+inline VEC dec2binary(int n, int p) {  // cpp-code/utils.cpp:73-89: p digits, most significant first
+  VEC b((size_t)p);
+  for (int j = 0; j < p; ++j) b[(size_t)j] = (n >> (p - 1 - j)) & 1;
+  return b;
+}
+inline std::vector<VEC> fd_binaries(int p) {  // cpp-code/utils.cpp:91-101: binaries of 1 .. 2^p - 1
+  std::vector<VEC> out;
+  for (int i = 1; i < (1 << p); ++i) out.push_back(dec2binary(i, p));
+  return out;
+}
+
 inline double prodd(const vec &a) {  // cpp-code/utils.cpp:24-30
   double p = 1.0;
   for (size_t i = 0; i < a.size(); ++i) p *= a[i];

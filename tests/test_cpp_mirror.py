@@ -30,6 +30,12 @@ def test_cpp_mirror_compiles_and_links(tmp_path, name):
         assert subprocess.run([exe]).returncode == 2
 
 
+def test_cpp_utils_known_answers(tmp_path):
+    """cpp-code/utils_test.cpp's printed known answers, asserted (host index maps: runs without a GPU)."""
+    r = subprocess.run([_build(tmp_path, "utils_test")], capture_output=True, text=True)
+    assert r.returncode == 0 and "utils_test ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_cpp_mirror_fails_loudly_without_gpu(tmp_path):
     """No CPU fallback behind the C++ interface either: without a device the first call throws."""
     import ctypes
