@@ -5,10 +5,12 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <memory>
 #include <vector>
 
@@ -131,6 +133,11 @@ struct mvtv_plan {
 
   double *staging = nullptr;
   size_t staging_bytes = 0;
+  // grow-only scratch of set_points (staged host inputs; sort keys + CUB temp) and capacity of vid: a plan that is
+  // re-binned (CV folds, repeated end-to-end calls) never goes back to cudaMalloc / cudaFree
+  void *in_buf = nullptr, *sort_buf = nullptr;
+  size_t in_bytes = 0, sort_bytes = 0;
+  long long vid_cap = 0;
   long long launches = 0;
   int last_cg_iters = 8;
   int last_cg_prec = 0;
@@ -182,6 +189,17 @@ struct mvtv_plan {
 
   void use_device() const { MVTV_CUDA(cudaSetDevice(device)); }
 
+  static void *grow(void *&buf, size_t &have, size_t bytes) {
+    if (bytes > have) {
+      if (buf) MVTV_CUDA(cudaFree(buf));
+      buf = nullptr;
+      have = 0;
+      MVTV_CUDA(cudaMalloc(&buf, bytes));
+      have = bytes;
+    }
+    return buf;
+  }
+
   double *stage(size_t bytes) {
     if (bytes > staging_bytes) {
       if (staging) MVTV_CUDA(cudaFree(staging));
@@ -207,7 +225,7 @@ struct mvtv_plan {
     if (cb) cudaFree(cb);
     if (d_peer) cudaFree(d_peer);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pbuf[0], pbuf[1], q, dinv, zbuf, u[0], u[1], S, zr, raw, partials, counters, vid, staging};
+    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pbuf[0], pbuf[1], q, dinv, zbuf, u[0], u[1], S, zr, raw, partials, counters, vid, staging, in_buf, sort_buf};
     for (void *b : bufs)
       if (b) cudaFree(b);
     if (h_scal) cudaFreeHost(h_scal);
@@ -516,42 +534,36 @@ struct mvtv_plan {
                     const double *y_dev, const double *axes_dev) {
     use_device();
     MVTV_REQUIRE(npts >= 1 && npts < (1ll << 31), "n must be in [1, 2^31)");
-    if (vid) MVTV_CUDA(cudaFree(vid));
-    vid = nullptr;
-    MVTV_CUDA(cudaMalloc(&vid, sizeof(long long) * (size_t)npts));
-    unsigned *key_in, *key_out, *val_in, *val_out;
-    void *temp;
-    const size_t tb = sort_temp_bytes(npts);
-    MVTV_CUDA(cudaMalloc(&key_in, sizeof(unsigned) * (size_t)npts * 4));
-    key_out = key_in + npts;
-    val_in = key_out + npts;
-    val_out = val_in + npts;
-    MVTV_CUDA(cudaMalloc(&temp, std::max<size_t>(tb, 16)));
-    try {
-      launch_bin(p, dt, npts, data_dev, ld_point, ld_axis, axes_dev, vid, key_in, val_in, stream);
-      launch_sort(temp, tb, npts, key_in, key_out, val_in, val_out, stream);
-      const size_t vb = (size_t)dt.usz * esz();
-      MVTV_CUDA(cudaMemsetAsync(oty, 0, vb, stream));
-      MVTV_CUDA(cudaMemsetAsync(cnt, 0, vb, stream));
-      launch_segment_reduce<T>(npts, key_out, val_out, y_dev, dt.plane, (T *)oty, (T *)cnt, stream);
-      launches += 5;
-      // mean(y) (cpp-code/solvers.cpp:95,103): deterministic two-level sum on the device
-      sum_y(y_dev, npts);
-      MVTV_CUDA(cudaStreamSynchronize(stream));
-      if (world > 1) {
-        // every rank must hold exactly the points of its own slab (partition.exchange_points)
-        unsigned last_key = 0;
-        MVTV_CUDA(cudaMemcpy(&last_key, key_out + (npts - 1), sizeof(unsigned), cudaMemcpyDeviceToHost));
-        if (last_key == 0xFFFFFFFFu)
-          throw Error(MVTV_ERR_INVALID, "world > 1: a point's nearest vertex lies outside this rank's slab");
-      }
-    } catch (...) {
-      cudaFree(key_in);
-      cudaFree(temp);
-      throw;
+    if (npts > vid_cap) {
+      if (vid) MVTV_CUDA(cudaFree(vid));
+      vid = nullptr;
+      vid_cap = 0;
+      MVTV_CUDA(cudaMalloc(&vid, sizeof(long long) * (size_t)npts));
+      vid_cap = npts;
     }
-    MVTV_CUDA(cudaFree(key_in));
-    MVTV_CUDA(cudaFree(temp));
+    have_points = false;   // a failure below must not leave a half-built operator behind
+    const size_t tb = sort_temp_bytes(npts);
+    const size_t kb = (sizeof(unsigned) * (size_t)npts * 4 + 255) & ~(size_t)255;
+    unsigned *key_in = (unsigned *)grow(sort_buf, sort_bytes, kb + std::max<size_t>(tb, 16));
+    unsigned *key_out = key_in + npts, *val_in = key_out + npts, *val_out = val_in + npts;
+    void *temp = (unsigned char *)key_in + kb;
+    launch_bin(p, dt, npts, data_dev, ld_point, ld_axis, axes_dev, vid, key_in, val_in, stream);
+    launch_sort(temp, tb, npts, key_in, key_out, val_in, val_out, stream);
+    const size_t vb = (size_t)dt.usz * esz();
+    MVTV_CUDA(cudaMemsetAsync(oty, 0, vb, stream));
+    MVTV_CUDA(cudaMemsetAsync(cnt, 0, vb, stream));
+    launch_segment_reduce<T>(npts, key_out, val_out, y_dev, dt.plane, (T *)oty, (T *)cnt, stream);
+    launches += 5;
+    // mean(y) (cpp-code/solvers.cpp:95,103): deterministic two-level sum on the device
+    sum_y(y_dev, npts);
+    MVTV_CUDA(cudaStreamSynchronize(stream));
+    if (world > 1) {
+      // every rank must hold exactly the points of its own slab (partition.exchange_points)
+      unsigned last_key = 0;
+      MVTV_CUDA(cudaMemcpy(&last_key, key_out + (npts - 1), sizeof(unsigned), cudaMemcpyDeviceToHost));
+      if (last_key == 0xFFFFFFFFu)
+        throw Error(MVTV_ERR_INVALID, "world > 1: a point's nearest vertex lies outside this rank's slab");
+    }
     exchange_ghosts<T>((T *)cnt);   // diag(c) on the ghost planes feeds the redundant ghost-plane work
     MVTV_CUDA(cudaStreamSynchronize(stream));
     dinv_rho = NAN;
@@ -1344,21 +1356,26 @@ int mvtv_plan_set_points_strided(mvtv_plan *plan, int64_t n, const double *data,
     long long na = 0;
     for (int a = 0; a < plan->p; ++a) na += plan->dt.m[a];
     const size_t nd = (size_t)n * plan->p, total = nd + (size_t)n + (size_t)na;
-    double *buf = nullptr;
-    MVTV_CUDA(cudaMalloc(&buf, sizeof(double) * total));
-    int rc = MVTV_OK;
-    try {
-      MVTV_CUDA(cudaMemcpyAsync(buf, data, sizeof(double) * nd, cudaMemcpyHostToDevice, plan->stream));
-      MVTV_CUDA(cudaMemcpyAsync(buf + nd, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, plan->stream));
-      MVTV_CUDA(cudaMemcpyAsync(buf + nd + n, axes, sizeof(double) * (size_t)na, cudaMemcpyHostToDevice, plan->stream));
-      if (plan->dtype == MVTV_F64) plan->set_points_t<double>(n, buf, ld_point, ld_axis, buf + nd, buf + nd + n);
-      else plan->set_points_t<float>(n, buf, ld_point, ld_axis, buf + nd, buf + nd + n);
-    } catch (...) {
-      cudaFree(buf);
-      throw;
+    const bool trace = getenv("MVTV_TRACE") != nullptr;   // wall-clock phases of the setup on stderr
+    const auto t0 = std::chrono::steady_clock::now();
+    double *buf = (double *)mvtv_plan::grow(plan->in_buf, plan->in_bytes, sizeof(double) * total);
+    const auto t1 = std::chrono::steady_clock::now();
+    MVTV_CUDA(cudaMemcpyAsync(buf, data, sizeof(double) * nd, cudaMemcpyHostToDevice, plan->stream));
+    MVTV_CUDA(cudaMemcpyAsync(buf + nd, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, plan->stream));
+    MVTV_CUDA(cudaMemcpyAsync(buf + nd + n, axes, sizeof(double) * (size_t)na, cudaMemcpyHostToDevice, plan->stream));
+    if (trace) MVTV_CUDA(cudaStreamSynchronize(plan->stream));
+    const auto t2 = std::chrono::steady_clock::now();
+    if (plan->dtype == MVTV_F64) plan->set_points_t<double>(n, buf, ld_point, ld_axis, buf + nd, buf + nd + n);
+    else plan->set_points_t<float>(n, buf, ld_point, ld_axis, buf + nd, buf + nd + n);
+    if (trace) {
+      const auto t3 = std::chrono::steady_clock::now();
+      auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+      };
+      fprintf(stderr, "[mvtv] set_points n=%lld: scratch %.2f ms, h2d %.2f ms (%.1f GB/s), bin+sort+reduce %.2f ms\n",
+              (long long)n, ms(t0, t1), ms(t1, t2), sizeof(double) * total / (ms(t1, t2) * 1e6), ms(t2, t3));
     }
-    MVTV_CUDA(cudaFree(buf));
-    return rc;
+    return MVTV_OK;
   });
 }
 
