@@ -119,15 +119,16 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def stage_bytes(N, R, esz):
-    """Algorithmic bytes per launch of each kernel class (DESIGN.md 'Kernels'): N = vertices, R = rows of D."""
+def stage_bytes(N, R, esz, prec_words=4):
+    """Algorithmic bytes per launch of each kernel class (DESIGN.md 'Kernels'): N = vertices, R = rows of D.
+    prec_words: 4 for k_cg_step<STEP_PREC> (reads r, dinv, c), 3 for k_cg_step2d (derives c from dinv)."""
     return {
         "zu": esz * (2 * R + 4 * N),      # read u, theta, theta_prev ; write u, D^T alpha, D^T u
         "cg_init": esz * (8 * N),         # read theta, c, dinv, Oty, v1, v2 ; write r, theta_old
         "cg_step": esz * (6 * N),         # read r, dinv, p_old, c ; write p_new, q
         "cg_update": esz * (7 * N),       # read theta, p, r, q, dinv ; write theta, r
         # MVTV_PRECOND_CHEB1 variants
-        "cg_prec": esz * (4 * N),         # read r, dinv, c ; write z
+        "cg_prec": esz * (prec_words * N),  # read r, dinv (, c) ; write z
         "cg_step_z": esz * (5 * N),       # read z, p_old, c ; write p_new, q
         "cg_update_p": esz * (6 * N),     # read theta, p, r, q ; write theta, r
     }
@@ -299,6 +300,7 @@ def run_ours(args):
 
     # every rank drops its plan (and NCCL communicator) at the same point: ncclCommDestroy is collective
     Nl_, R_, Nfull_ = plan.n_local, plan.R, plan.N
+    kernels = plan.describe()
     plan.close()
     if rank != 0:
         if dist:
@@ -309,7 +311,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
     Nl, Rl = Nl_, R_ * Nl_ / max(1, Nfull_)   # rows scale with the slab
-    sb = stage_bytes(Nl, Rl, esz)
+    sb = stage_bytes(Nl, Rl, esz, kernels["cg_prec_words"])
     if args.precond == "cheb1":
         sb["cg_step"], sb["cg_update"] = sb["cg_step_z"], sb["cg_update_p"]
     performed = {"zu": passes, "cg_init": passes, "cg_step": inner, "cg_update": inner, "cg_prec": inner}
@@ -323,12 +325,16 @@ def run_ours(args):
     dom = max(stages, key=lambda k: stages[k]["total_ms"]) if stages else None
     # DRAM traffic of the same kernel from the committed ncu --set full capture of this workload (per launch)
     traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_final_ncu_traffic.json")))
-        if world == 1 and args.dtype == "f64" and dom in tr.get(args.workload, {}):
-            traffic = tr[args.workload][dom]["dram_bytes_per_launch"]
-    except Exception:
-        traffic = None
+    for tf in ("r1_final2_ncu_traffic.json", "r1_final_ncu_traffic.json"):   # newest capture first
+        try:
+            ent = json.load(open(os.path.join(ROOT, "profiles", tf))).get(args.workload, {}).get(dom)
+        except Exception:
+            ent = None
+        # only a capture of the kernel that actually ran counts (cg_step / cg_prec exist in two implementations)
+        runs = kernels.get(dom, "k_" + str(dom)) + "<"
+        if ent and world == 1 and args.dtype == "f64" and ent.get("kernel", "").startswith(runs):
+            traffic = ent["dram_bytes_per_launch"]
+            break
     roof = None
     if dom:
         roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
@@ -347,6 +353,7 @@ def run_ours(args):
         "config": {"workload": wl["desc"] + (" per GPU (weak: last axis x%d)" % world if world > 1 and args.scaling == "weak" else ""),
                    "mesh": m, "n_points": n * (world if args.scaling == "weak" else 1), "mode": mode, "lambda": args.lam,
                    "cg_rtol": args.cg_rtol, "precond": args.precond, "parallelism": "slab%d" % world,
+                   "kernels": {k: kernels[k] for k in ("zu", "cg_step", "cg_prec", "collectives")},
                    "l2": "working set per pass (u: %.2f GB) exceeds the 126 MB L2" % (2 * Rl * esz / 1e9)},
         "admm_iters_per_sec": passes / dev_s, "inner_cg_iters_per_pass": J,
         "pass_alg_bytes": b_iter, "pass_gbs": b_iter / (dev_s / passes) / 1e9, "pass_frac_of_peak": b_iter / (dev_s / passes) / 1e9 / peak,

@@ -146,6 +146,10 @@ int mvtv_plan_set_points_strided(mvtv_plan *plan, int64_t n, const double *data,
 /* Same with inputs already resident in HBM (device pointers on the plan's device). */
 int mvtv_plan_set_points_dev(mvtv_plan *plan, int64_t n, const double *data_colmajor_dev,
                              const double *y_dev, const double *axes_dev);
+/* Which kernels this plan runs, as a small JSON object (zu: k_zu_march | k_zu; cg_step / cg_prec: k_cg_step |
+ * k_cg_step2d; cg_prec_words: words of HBM traffic per vertex of the preconditioner kernel; collectives: none | peer |
+ * nccl).  bench.py uses it for the algorithmic bytes of each kernel class. */
+int mvtv_plan_describe(const mvtv_plan *plan, char *buf, int64_t cap);
 /* Per-kernel-class CUDA-event timing on the plan's stream (used by bench.py for the roofline).
  * ms[k], count[k], k = MVTV_KC_*: accumulated milliseconds and number of launches since enable. */
 #define MVTV_KC_ZU 0        /* fused z/u update + D^T products + norms */

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmvtv_b200.so")
 
 SYMBOLS = [
     "mvtv_abi_version", "mvtv_last_error", "mvtv_device_count", "mvtv_nccl_unique_id", "mvtv_host_alloc", "mvtv_host_free", "mvtv_plan_create", "mvtv_plan_destroy",
-    "mvtv_plan_info", "mvtv_plan_profile", "mvtv_plan_get_profile", "mvtv_plan_set_points", "mvtv_plan_set_points_strided", "mvtv_plan_set_points_dev", "mvtv_plan_get_cache", "mvtv_solve", "mvtv_solve_path", "mvtv_lambda_max",
+    "mvtv_plan_info", "mvtv_plan_describe", "mvtv_plan_profile", "mvtv_plan_get_profile", "mvtv_plan_set_points", "mvtv_plan_set_points_strided", "mvtv_plan_set_points_dev", "mvtv_plan_get_cache", "mvtv_solve", "mvtv_solve_path", "mvtv_lambda_max",
     "mvtv_predict", "mvtv_apply_D", "mvtv_apply_Dt", "mvtv_apply_M", "mvtv_softthresh", "mvtv_adapt_step", "mvtv_nearest",
 ]
 
@@ -82,6 +82,7 @@ def load():
     L.mvtv_plan_create.argtypes = [C.POINTER(vp), C.POINTER(PlanDesc)]
     L.mvtv_plan_destroy.argtypes = [vp]
     L.mvtv_plan_info.argtypes = [vp, ip, ip, ip, ip]
+    L.mvtv_plan_describe.argtypes = [vp, C.c_char_p, C.c_int64]
     L.mvtv_plan_profile.argtypes = [vp, C.c_int]
     L.mvtv_plan_get_profile.argtypes = [vp, dp, ip]
     L.mvtv_plan_set_points.argtypes = [vp, C.c_int64, dp, dp, dp]

@@ -14,6 +14,7 @@
 #include <memory>
 #include <vector>
 
+#include "cg_step2d.cuh"
 #include "kernels.cuh"
 #include "setup.h"
 #include "zu_march.cuh"
@@ -147,6 +148,8 @@ struct mvtv_plan {
   std::vector<void *> ipc_opened;
   unsigned long long red_seq = 0, halo_seq = 0, zhalo_seq = 0;
   double cheb_bmax = 0.0;   // bound on the spectrum of D^-1 (diag(c) + s D^T D), independent of s and c
+  int step2d_cfg = 0, step2d_prec_cfg = 0;   // tile variants of k_cg_step2d (MVTV_STEP2D_CFG, MVTV_STEP2D_PREC_CFG)
+  bool step2d = false;   // 2-D meshes: shuffle-based k_cg_step2d (cg_step2d.cuh) instead of the shared-memory k_cg_step
   int zu_variant = -1;   // ZV_* when the compile-time block tables of k_zu_march match this plan, else -1 (gather kernel)
 
   // optional per-kernel-class CUDA-event timing on the plan's stream (mvtv_plan_profile)
@@ -320,6 +323,16 @@ struct mvtv_plan {
       for (int b = 0; same && b < K; ++b) same = (zu_block_mask(P, V, b) == bt.mask[b]);
       const char *env = getenv("MVTV_ZU_KERNEL");
       zu_variant = (same && !(env && std::string(env) == "gather")) ? V : -1;
+    }
+
+    {
+      const char *env = getenv("MVTV_STEP2D");
+      const bool want = !(env && std::string(env) == "smem");   // MVTV_STEP2D=smem forces the shared-memory k_cg_step
+      step2d = want && P == 2 && (m[0] % 2 == 0) && m[0] >= 2;
+      const char *c2 = getenv("MVTV_STEP2D_CFG");
+      step2d_cfg = c2 ? atoi(c2) : 0;
+      const char *c3 = getenv("MVTV_STEP2D_PREC_CFG");
+      step2d_prec_cfg = c3 ? atoi(c3) : 0;
     }
 
     // 3^P-point stencil of D^T D = sum_b c_b^2 kron_{a in S'_b} L_a  (SURVEY A.6), clamped indices
@@ -864,8 +877,64 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     return dim3(tiles, (unsigned)nchunk, 1);
   };
   int zchunk = 1, zchunk_prec = 1;
-  const dim3 gs = chunking(occ3[prec ? STEP_Z : STEP_JACOBI], zchunk);
-  const dim3 gs_prec = chunking(occ3[STEP_PREC], zchunk_prec);
+  dim3 gs = chunking(occ3[prec ? STEP_Z : STEP_JACOBI], zchunk);
+  dim3 gs_prec = chunking(occ3[STEP_PREC], zchunk_prec);
+  // 2-D meshes with an even m0: the shuffle-based kernel (no shared memory), one 64-vertex strip per warp
+  const bool use2d = (P == 2) && step2d;
+  // tile variants: warps per CTA, rows in flight per lane, vertices per lane, resident CTAs asked of the compiler.
+  // The direction + SpMV kernel (5-6 N words) and the preconditioner kernel (3 N words) have different sweet spots.
+  auto dispatch2d = [&](auto &&fn) {          // STEP_JACOBI / STEP_Z (MVTV_STEP2D_CFG)
+    switch (step2d_cfg) {
+      case 1: fn(Step2dCfg<8, 1, 2, 4>{}); break;
+      case 2: fn(Step2dCfg<8, 1, 4, 2>{}); break;
+      case 3: fn(Step2dCfg<8, 1, 2, 3>{}); break;
+      case 4: fn(Step2dCfg<4, 2, 2, 0>{}); break;
+      default: fn(Step2dCfg<4, 1, 4, 0>{}); break;
+    }
+  };
+  auto dispatch2d_prec = [&](auto &&fn) {     // STEP_PREC (MVTV_STEP2D_PREC_CFG)
+    switch (step2d_prec_cfg) {
+      case 1: fn(Step2dCfg<8, 1, 2, 5, true>{}); break;
+      case 2: fn(Step2dCfg<8, 1, 2, 6, true>{}); break;
+      case 3: fn(Step2dCfg<16, 1, 2, 2, true>{}); break;
+      case 4: fn(Step2dCfg<4, 1, 2, 8, true>{}); break;
+      case 5: fn(Step2dCfg<8, 1, 2, 4, false>{}); break;   // reads diag(c) like k_cg_step (4 N words)
+      default: fn(Step2dCfg<8, 1, 2, 4, true>{}); break;
+    }
+  };
+  auto chunking2 = [&](unsigned tiles2, int occ, int &zchunk_out) {
+    const long long slots = (long long)nsm * std::max(occ, 1);
+    int nchunk = 1;
+    double best = -1.0;
+    const int maxchunk = std::max(1, std::min(dt.nz / 16, 4096));
+    for (int nc = 1; nc <= maxchunk; ++nc) {
+      const int zc = (dt.nz + nc - 1) / nc;
+      const int ncr = (dt.nz + zc - 1) / zc;
+      const long long total = (long long)tiles2 * ncr;
+      if (total > (1ll << 16)) break;
+      const long long waves = (total + slots - 1) / slots;
+      const double eff = (double)total / (double)(waves * slots) * ((double)zc / (zc + 2.0));
+      if (eff > best + 1e-9) { best = eff; nchunk = ncr; }
+    }
+    zchunk_out = (dt.nz + nchunk - 1) / nchunk;
+    nchunk = (dt.nz + zchunk_out - 1) / zchunk_out;
+    return dim3(tiles2, (unsigned)nchunk, 1);
+  };
+  if (use2d) {
+    dispatch2d([&](auto cfg) {
+      using C2 = decltype(cfg);
+      int occ = 1;
+      if (prec) MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step2d<T, C2, STEP_Z>, C2::NT, 0));
+      else MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step2d<T, C2, STEP_JACOBI>, C2::NT, 0));
+      gs = chunking2((unsigned)((m0 + C2::TX - 1) / C2::TX), occ, zchunk);
+    });
+    if (prec) dispatch2d_prec([&](auto cfg) {
+      using C2 = decltype(cfg);
+      int occ = 1;
+      MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step2d<T, C2, STEP_PREC>, C2::NT, 0));
+      gs_prec = chunking2((unsigned)((m0 + C2::TX - 1) / C2::TX), occ, zchunk_prec);
+    });
+  }
   const int gu = (int)std::max<long long>(1, std::min<long long>(148 * 8, (dt.Nloc + 1023) / 1024));
   int launched = 0;
   int batch = std::max(2, std::min(last_cg_iters, 256));
@@ -877,7 +946,11 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
         a.seq_red = ++red_seq;
         a.seq_zhalo = ++zhalo_seq;
         prof_begin(MVTV_KC_CG_PREC);
-        k_cg_step<T, Cfg, STEP_PREC><<<gs_prec, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
+        if (use2d) dispatch2d_prec([&](auto cfg) {
+          using C2 = decltype(cfg);
+          k_cg_step2d<T, C2, STEP_PREC><<<gs_prec, C2::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
+        });
+        else k_cg_step<T, Cfg, STEP_PREC><<<gs_prec, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
         prof_end();
         if (d_peer) {
           k_cg_peer_commit_rz<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
@@ -890,7 +963,13 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       }
       a.seq_red = ++red_seq;       // a.seq_halo: the version the last producer of r posted
       prof_begin(MVTV_KC_CG_STEP);
-      if (prec) k_cg_step<T, Cfg, STEP_Z><<<gs, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+      if (use2d) {
+        dispatch2d([&](auto cfg) {
+          using C2 = decltype(cfg);
+          if (prec) k_cg_step2d<T, C2, STEP_Z><<<gs, C2::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+          else k_cg_step2d<T, C2, STEP_JACOBI><<<gs, C2::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+        });
+      } else if (prec) k_cg_step<T, Cfg, STEP_Z><<<gs, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       else k_cg_step<T, Cfg, STEP_JACOBI><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       prof_end();
       if (d_peer) {
@@ -1310,6 +1389,23 @@ int mvtv_plan_info(const mvtv_plan *plan, int64_t *N, int64_t *R, int64_t *z0, i
     if (R) *R = plan->rt.R;
     if (z0) *z0 = plan->dt.z0;
     if (nz) *nz = plan->dt.nz;
+    return MVTV_OK;
+  });
+}
+
+int mvtv_plan_describe(const mvtv_plan *plan, char *buf, int64_t cap) {
+  return guarded([&] {
+    MVTV_REQUIRE(plan && buf && cap > 0, "null argument");
+    const bool s2 = plan->step2d && plan->dt.P == 2;
+    char tmp[512];
+    snprintf(tmp, sizeof(tmp),
+             "{\"p\": %d, \"dtype\": %d, \"world\": %d, \"zu\": \"%s\", \"cg_step\": \"%s\", \"cg_prec\": \"%s\", "
+             "\"cg_prec_words\": %d, \"collectives\": \"%s\"}",
+             plan->p, plan->dtype, plan->world, plan->zu_variant >= 0 ? "k_zu_march" : "k_zu",
+             s2 ? "k_cg_step2d" : "k_cg_step", s2 ? "k_cg_step2d" : "k_cg_step", s2 ? 3 : 4,
+             plan->world == 1 ? "none" : (plan->d_peer ? "peer" : "nccl"));
+    MVTV_REQUIRE((int64_t)strlen(tmp) < cap, "buffer too small");
+    strcpy(buf, tmp);
     return MVTV_OK;
   });
 }

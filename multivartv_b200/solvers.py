@@ -358,6 +358,13 @@ class Plan:
         _lib.check(_lib.load().mvtv_predict(self._h, n, _dp(dcm), _dp(ax), _dp(th), _dp(out)))
         return out
 
+    def describe(self):
+        """Which kernels this plan runs (mvtv_plan_describe) as a dict."""
+        import json
+        buf = C.create_string_buffer(1024)
+        _lib.check(_lib.load().mvtv_plan_describe(self._h, buf, 1024))
+        return json.loads(buf.value.decode())
+
     def profile(self, enable=True):
         _lib.check(_lib.load().mvtv_plan_profile(self._h, 1 if enable else 0))
 

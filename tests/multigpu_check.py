@@ -35,6 +35,8 @@ def main():
              ([40, 40, 40], 64000, "rcpp", 1.0, 15, J), ([24, 22], 3000, "rcpp", 1.0, 0, C1),
              ([12, 12, 13], 4000, "rcpp", 0.7, 0, C1), ([8, 8, 8, 9], 5000, "rcpp", 1.0, 25, C1),
              ([40, 40, 40], 64000, "rcpp", 1.0, 15, C1)]
+    if os.environ.get("MVTV_MG_ONLY2D"):   # short run: the 2-D cases only (k_cg_step2d's ghost-row / peer-memory protocol)
+        cases = [c for c in cases if len(c[0]) == 2 and c[2] != "py"] + [([64, 64], 20000, "rcpp", 0.8, 40, C1)]
     for dims, n, mode, lam, max_passes, precond in cases:
         p = len(dims)
         imode = {"cpp": 0, "rcpp": 1, "py": 2}[mode]

@@ -508,3 +508,35 @@ def test_gather_kernel_cross_check(mv, monkeypatch):
         assert a["counter"] == b["counter"]
         assert np.abs(a["theta"] - b["theta"]).max() <= 1e-12
         assert np.abs(a["u"] - b["u"]).max() <= 1e-11
+
+
+def test_step2d_kernel_cross_check(mv, monkeypatch):
+    """k_cg_step (shared-memory ring) and k_cg_step2d (warp shuffles, no shared memory; its preconditioner variant never
+    reads diag(c)) are two implementations of the fused CG direction + SpMV on 2-D meshes: same passes, theta within
+    1e-10 of each other and within 1e-9 of the oracle, on widths that are / are not multiples of the 64- and 128-vertex
+    strips, for both preconditioners; odd widths fall back to k_cg_step."""
+    for dims, n in ([100, 37], 3000), ([66, 5], 400), ([2, 9], 60), ([258, 33], 9000), ([130, 64], 5000):
+        x, y = synth(80 + dims[0], n, 2, 0.0, 1.0, 0.5)
+        axes = po.mesh_axes(x, dims, po.MODE_RCPP)
+        for precond in (mv.PRECOND_CHEB1, mv.PRECOND_JACOBI):
+            res = {}
+            for which in ("shfl", "smem"):
+                monkeypatch.setenv("MVTV_STEP2D", which)
+                with mv.Plan(dims) as pl:
+                    assert pl.describe()["cg_step"] == ("k_cg_step2d" if which == "shfl" else "k_cg_step")
+                    pl.set_points(x, y, axes)
+                    res[which] = pl.solve(0.8, mode="rcpp", max_passes=40, precond=precond)
+            monkeypatch.delenv("MVTV_STEP2D", raising=False)
+            assert res["shfl"]["passes"] == res["smem"]["passes"]
+            assert np.abs(res["shfl"]["theta"] - res["smem"]["theta"]).max() <= 1e-10
+        ref = co.mbs_one(x, y, dims, axes, 0.8, mode=co.MODE_RCPP, max_passes=40)
+        assert np.abs(res["shfl"]["theta"] - ref["theta"]).max() <= FP64_TOL
+    monkeypatch.delenv("MVTV_STEP2D", raising=False)
+    with mv.Plan([33, 20]) as pl:                       # odd width: rows are not 16-byte aligned
+        d = pl.describe()
+        assert d["cg_step"] == "k_cg_step" and d["cg_prec_words"] == 4
+    with mv.Plan([32, 20]) as pl:
+        d = pl.describe()
+        assert d["cg_step"] == "k_cg_step2d" and d["cg_prec_words"] == 3 and d["collectives"] == "none"
+    with mv.Plan([8, 8, 8]) as pl:
+        assert pl.describe()["cg_step"] == "k_cg_step"
