@@ -39,10 +39,11 @@ __device__ __forceinline__ void st2(T *__restrict__ p, T a, T b) {
 // WARPS per CTA, PF rows in flight per lane, VPL vertices per lane (2 or 4: one or two 16-byte accesses per array and
 // row), MINB = minimum resident CTAs per SM asked of the compiler (0: none), NOC: STEP_PREC derives diag(c) from dinv
 // instead of reading it (dinv*c = 1 - dinv*rhoM*diag(K)), i.e. 3 N words instead of 4 N.
-template <int WARPS_, int PF_, int VPL_ = 2, int MINB_ = 0, bool NOC_ = false>
+// DKSEL: NOC picks diag(K) of a vertex with selects on constant-bank operands instead of holding 2*VPL values in registers.
+template <int WARPS_, int PF_, int VPL_ = 2, int MINB_ = 0, bool NOC_ = false, bool DKSEL_ = false>
 struct Step2dCfg {
   static constexpr int WARPS = WARPS_, PF = PF_, VPL = VPL_, NG = VPL_ / 2, MINB = MINB_;
-  static constexpr bool NOC = NOC_;
+  static constexpr bool NOC = NOC_, DKSEL = DKSEL_;
   static constexpr int NT = 32 * WARPS_, SW = 32 * VPL_, TX = SW * WARPS_;
   static_assert(VPL_ == 2 || VPL_ == 4, "two or four vertices per lane");
 };
@@ -94,12 +95,15 @@ k_cg_step2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
     __syncthreads();
   }
   // NOC: diag(K) of this lane's vertices for an interior row and for a boundary row of the marching axis
+  constexpr bool DKSEL = Cfg::DKSEL;
   T dKi[VPL], dKb[VPL];
+  bool bxk[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const bool bx = (x + k == 0 || x + k == m0 - 1);
-    dKi[k] = NOC ? (T)(bx ? st.diagK[1] : st.diagK[0]) : T(0);
-    dKb[k] = NOC ? (T)(bx ? st.diagK[3] : st.diagK[2]) : T(0);
+    bxk[k] = bx;
+    dKi[k] = (NOC && !DKSEL) ? (T)(bx ? st.diagK[1] : st.diagK[0]) : T(0);
+    dKb[k] = (NOC && !DKSEL) ? (T)(bx ? st.diagK[3] : st.diagK[2]) : T(0);
   }
 
   // register ring: raw inputs of PF rows in flight
@@ -198,7 +202,9 @@ k_cg_step2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
             if (MODE == STEP_PREC) {
               T zv;
               if (NOC) {   // dinv*q = z0 + dinv*rhoM*(K z0 - diag(K) z0): diag(c) never read
-                zv = (T)(a.pc0 + a.pc1) * pv + (T)a.pc1 * (rhoM * dcp[k] * (A0[k] - (bz ? dKb[k] : dKi[k]) * pv));
+                const T dk = DKSEL ? (T)(bz ? (bxk[k] ? st.diagK[3] : st.diagK[2]) : (bxk[k] ? st.diagK[1] : st.diagK[0]))
+                                   : (bz ? dKb[k] : dKi[k]);
+                zv = (T)(a.pc0 + a.pc1) * pv + (T)a.pc1 * (rhoM * dcp[k] * (A0[k] - dk * pv));
               } else {
                 const T qv = cqp[k] * pv + rhoM * A0[k];
                 zv = (T)a.pc0 * pv + (T)a.pc1 * (dcp[k] * qv);

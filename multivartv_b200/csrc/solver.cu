@@ -899,6 +899,9 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       case 3: fn(Step2dCfg<16, 1, 2, 2, true>{}); break;
       case 4: fn(Step2dCfg<4, 1, 2, 8, true>{}); break;
       case 5: fn(Step2dCfg<8, 1, 2, 4, false>{}); break;   // reads diag(c) like k_cg_step (4 N words)
+      case 6: fn(Step2dCfg<8, 1, 2, 4, true, true>{}); break;
+      case 7: fn(Step2dCfg<8, 1, 2, 3, true, true>{}); break;
+      case 8: fn(Step2dCfg<8, 1, 2, 3, true, false>{}); break;
       default: fn(Step2dCfg<8, 1, 2, 4, true>{}); break;
     }
   };

@@ -24,34 +24,39 @@ def run(m, x, y, axes, env, passes, precond, dtype=mv.F64):
     return r, prof
 
 
-# ---- parity of the two kernels on awkward shapes ---------------------------------------------------------------
-for m, n in (([32, 32], 1000), ([100, 37], 3000), ([66, 5], 400), ([2, 9], 60), ([130, 64], 5000), ([258, 33], 9000)):
-    x, y = synth_points(n, 2, 5)
-    axes = [np.linspace(0.0, 1.0, d) for d in m]
-    for precond in (mv.PRECOND_CHEB1, mv.PRECOND_JACOBI):
-        ref, _ = run(m, x, y, axes, {"MVTV_STEP2D": "smem"}, 12, precond)
-        for cfg in range(6):
-            got, _ = run(m, x, y, axes, {"MVTV_STEP2D": "shfl", "MVTV_STEP2D_CFG": str(cfg % 5), "MVTV_STEP2D_PREC_CFG": str(cfg)}, 12, precond)
-            err = float(np.abs(got["theta"] - ref["theta"]).max())
-            ok = err <= 1e-10 and got["passes"] == ref["passes"]
-            print("parity m=%s precond=%d cfg=%d: max|dtheta|=%.2e inner %d vs %d %s" % (m, precond, cfg, err, got["inner_iters"], ref["inner_iters"], "ok" if ok else "MISMATCH"), flush=True)
-    r32, _ = run(m, x, y, axes, {"MVTV_STEP2D": "smem"}, 12, mv.PRECOND_CHEB1, mv.F32)
-    g32, _ = run(m, x, y, axes, {"MVTV_STEP2D": "shfl"}, 12, mv.PRECOND_CHEB1, mv.F32)
-    print("parity f32 m=%s: max|dtheta|=%.2e" % (m, float(np.abs(g32["theta"] - r32["theta"]).max())), flush=True)
+def main():
+    # ---- parity of the two kernels on awkward shapes ---------------------------------------------------------------
+    for m, n in (([32, 32], 1000), ([100, 37], 3000), ([66, 5], 400), ([2, 9], 60), ([130, 64], 5000), ([258, 33], 9000)):
+        x, y = synth_points(n, 2, 5)
+        axes = [np.linspace(0.0, 1.0, d) for d in m]
+        for precond in (mv.PRECOND_CHEB1, mv.PRECOND_JACOBI):
+            ref, _ = run(m, x, y, axes, {"MVTV_STEP2D": "smem"}, 12, precond)
+            for cfg in range(6):
+                got, _ = run(m, x, y, axes, {"MVTV_STEP2D": "shfl", "MVTV_STEP2D_CFG": str(cfg % 5), "MVTV_STEP2D_PREC_CFG": str(cfg)}, 12, precond)
+                err = float(np.abs(got["theta"] - ref["theta"]).max())
+                ok = err <= 1e-10 and got["passes"] == ref["passes"]
+                print("parity m=%s precond=%d cfg=%d: max|dtheta|=%.2e inner %d vs %d %s" % (m, precond, cfg, err, got["inner_iters"], ref["inner_iters"], "ok" if ok else "MISMATCH"), flush=True)
+        r32, _ = run(m, x, y, axes, {"MVTV_STEP2D": "smem"}, 12, mv.PRECOND_CHEB1, mv.F32)
+        g32, _ = run(m, x, y, axes, {"MVTV_STEP2D": "shfl"}, 12, mv.PRECOND_CHEB1, mv.F32)
+        print("parity f32 m=%s: max|dtheta|=%.2e" % (m, float(np.abs(g32["theta"] - r32["theta"]).max())), flush=True)
 
-# ---- timing on BASELINE configs[1] ------------------------------------------------------------------------------
-m, n = [4096, 4096], 1 << 24
-x, y = synth_points(n, 2, 117)
-axes = [np.linspace(0.0, 1.0, d) for d in m]
-for precond, pname in ((mv.PRECOND_CHEB1, "cheb1"), (mv.PRECOND_JACOBI, "jacobi")):
-    variants = [("smem", {"MVTV_STEP2D": "smem"})] + [("shfl%d" % c, {"MVTV_STEP2D": "shfl", "MVTV_STEP2D_CFG": str(c % 5), "MVTV_STEP2D_PREC_CFG": str(c)}) for c in (range(6) if pname == "cheb1" else range(5))]
-    for name, env in variants:
-        r, prof = run(m, x, y, axes, env, 10, precond)
-        inner = r["inner_iters"]
-        per = {k: (1e3 * v[0] / max(1, inner if k.startswith("cg_") and k != "cg_init" else r["passes"])) for k, v in prof.items() if v[1]}
-        print("time %s %-6s ms/pass=%.3f inner/pass=%.1f  us/launch: %s" % (pname, name, 1e3 * r["device_seconds"] / r["passes"], inner / r["passes"],
-              " ".join("%s=%.1f" % (k, v) for k, v in per.items())), flush=True)
-for dtype, dname in ((mv.F32, "f32"),):
-    for name, env in (("smem", {"MVTV_STEP2D": "smem"}), ("shfl0", {"MVTV_STEP2D": "shfl"}), ("shfl1", {"MVTV_STEP2D": "shfl", "MVTV_STEP2D_CFG": "1", "MVTV_STEP2D_PREC_CFG": "1"})):
-        r, prof = run(m, x, y, axes, env, 10, mv.PRECOND_CHEB1, dtype)
-        print("time %s %-6s ms/pass=%.3f inner/pass=%.1f" % (dname, name, 1e3 * r["device_seconds"] / r["passes"], r["inner_iters"] / r["passes"]), flush=True)
+    # ---- timing on BASELINE configs[1] ------------------------------------------------------------------------------
+    m, n = [4096, 4096], 1 << 24
+    x, y = synth_points(n, 2, 117)
+    axes = [np.linspace(0.0, 1.0, d) for d in m]
+    for precond, pname in ((mv.PRECOND_CHEB1, "cheb1"), (mv.PRECOND_JACOBI, "jacobi")):
+        variants = [("smem", {"MVTV_STEP2D": "smem"})] + [("shfl%d" % c, {"MVTV_STEP2D": "shfl", "MVTV_STEP2D_CFG": str(c % 5), "MVTV_STEP2D_PREC_CFG": str(c)}) for c in (range(6) if pname == "cheb1" else range(5))]
+        for name, env in variants:
+            r, prof = run(m, x, y, axes, env, 10, precond)
+            inner = r["inner_iters"]
+            per = {k: (1e3 * v[0] / max(1, inner if k.startswith("cg_") and k != "cg_init" else r["passes"])) for k, v in prof.items() if v[1]}
+            print("time %s %-6s ms/pass=%.3f inner/pass=%.1f  us/launch: %s" % (pname, name, 1e3 * r["device_seconds"] / r["passes"], inner / r["passes"],
+                  " ".join("%s=%.1f" % (k, v) for k, v in per.items())), flush=True)
+    for dtype, dname in ((mv.F32, "f32"),):
+        for name, env in (("smem", {"MVTV_STEP2D": "smem"}), ("shfl0", {"MVTV_STEP2D": "shfl"}), ("shfl1", {"MVTV_STEP2D": "shfl", "MVTV_STEP2D_CFG": "1", "MVTV_STEP2D_PREC_CFG": "1"})):
+            r, prof = run(m, x, y, axes, env, 10, mv.PRECOND_CHEB1, dtype)
+            print("time %s %-6s ms/pass=%.3f inner/pass=%.1f" % (dname, name, 1e3 * r["device_seconds"] / r["passes"], r["inner_iters"] / r["passes"]), flush=True)
+
+
+if __name__ == "__main__":
+    main()
