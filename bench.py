@@ -153,9 +153,30 @@ def cpu_baseline(args, threads=0, passes=2, warm=0):
                 seconds=r["seconds"], passes=r["passes"], inner_cg_iters=r["inner_iters"])
 
 
+def reference_compiled_config1():
+    """The reference's OWN compiled cpp-code solver (oracle/_ref, built from /root/reference against the Armadillo stand-in)
+    on BASELINE configs[0] (2-D, n = 1000 points, 32 x 32 mesh, lambda = 1.5) -- informational: upstream's O(n N) nearest
+    search and per-pass factorisation make it unusable at the benchmark's sizes."""
+    try:
+        from oracle import ref_oracle as ro
+        if not (os.path.exists(ro.LIB) and os.path.exists(ro.LIB_RCPP)):
+            return None
+        from tests.helpers import synth
+        x, y = synth(117, 1000, 2)
+        t0 = time.perf_counter()
+        r = ro.mbs_one(x, y, [32, 32], 1.5)
+        dt = time.perf_counter() - t0
+        passes = r["counter"] - 1
+        return {"what": "cpp-code mbs_one (set-up + %d ADMM passes) on configs[0], single thread" % passes, "seconds": dt,
+                "counter": r["counter"], "vertex_updates_per_s": 1024 * passes / dt}
+    except Exception as e:   # informational only
+        return {"error": str(e)[:200]}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  Armadillo/SuperLU are not installable here, so this times
-    the oracle port with all host threads on the bounded sample (rank 0 only)."""
+    """--impl reference: the reference's CPU path.  Upstream's own code (oracle/_ref) cannot run the benchmark's sizes
+    (O(n N) nearest search), so the timed value is the oracle port with all host threads on the bounded sample (rank 0
+    only); the compiled reference is timed on BASELINE configs[0] beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -171,7 +192,7 @@ def run_reference(args):
         "admm_iters_per_sec": cb["passes"] / cb["seconds"],
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "vertex-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "sample_vertices": N,
+        "gpu_launches": 0, "sample_vertices": N, "reference_compiled_config1": reference_compiled_config1(),
     }
     print(json.dumps(line), flush=True)
 

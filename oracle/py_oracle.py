@@ -9,17 +9,16 @@ repository root).  D is *materialised* as a scipy sparse matrix exactly the way 
 materialises it (``build_diffmat`` -> ``mixedpartial`` -> ``create_D``) and the x-update uses
 scipy's bundled SuperLU (``splu``), the same solver family as ``arma::spsolve``.
 
-Pinning status (see DESIGN.md "Oracle"):
+Pinning status (see DESIGN.md "Oracle" and oracle/README.md):
   * operators (index maps, masks, D incl. the mixedpartial direction-0 quirk, nearest, O, mesh)
-    are pinned against the reference's own Python prototype executed in this container
-    (tests/golden/make_golden.py -> tests/golden/*.npz) and against the known answers of
-    code/test_utils.py and cpp-code/utils_test.cpp;
-  * the PY solver mode (code/solvers.py:54-76) is pinned the same way (golden theta vectors);
-  * the CPP and RCPP solver loops (cpp-code/solvers.cpp:90-130, rcpp solvers.cpp:96-136) cannot be
-    compiled here (no Armadillo/SuperLU/R) and the reference's C++ tests assert nothing:
-    PARITY UNPINNED for those two loops beyond (a) sharing every operator and the PY-mode loop
-    skeleton with the pinned parts and (b) agreement of two independent restatements
-    (this file and oracle/c/mvtv_oracle.c).
+    and the PY solver mode (code/solvers.py:54-76) are pinned against the reference's own Python
+    prototype executed in this container (tests/golden/make_golden.py -> tests/golden/ref_py_golden.npz)
+    and against the known answers of code/test_utils.py and cpp-code/utils_test.cpp;
+  * the CPP and RCPP solver loops (cpp-code/solvers.cpp:90-130, rcpp solvers.cpp:96-136), create_D,
+    create_mesh, nearest1, adapt_step, mbs_path and mbs_impl are pinned against the reference's own
+    C++ sources compiled where they lie (oracle/_ref, built by oracle/ref_shim/Makefile against the
+    Armadillo / Rcpp stand-ins of oracle/arma_shim): identical Counter, theta within 1e-10
+    (tests/test_oracle_vs_reference.py, tests/test_golden_ref_cpp.py).
 """
 from __future__ import annotations
 
