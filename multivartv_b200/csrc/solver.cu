@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "cg_step2d.cuh"
+#include "cg_step3d.cuh"
 #include "kernels.cuh"
 #include "setup.h"
 #include "zu_march.cuh"
@@ -149,6 +150,8 @@ struct mvtv_plan {
   unsigned long long red_seq = 0, halo_seq = 0, zhalo_seq = 0;
   double cheb_bmax = 0.0;   // bound on the spectrum of D^-1 (diag(c) + s D^T D), independent of s and c
   int step2d_cfg = 0, step2d_prec_cfg = 0;   // tile variants of k_cg_step2d (MVTV_STEP2D_CFG, MVTV_STEP2D_PREC_CFG)
+  bool step3d = false;   // 3-D meshes: EXPERIMENTAL shuffle-based k_cg_step3d (MVTV_STEP3D=shfl), default off
+  int step3d_cfg = 0;
   bool step2d = false;   // 2-D meshes: shuffle-based k_cg_step2d (cg_step2d.cuh) instead of the shared-memory k_cg_step
   int zu_variant = -1;   // ZV_* when the compile-time block tables of k_zu_march match this plan, else -1 (gather kernel)
 
@@ -333,6 +336,10 @@ struct mvtv_plan {
       step2d_cfg = c2 ? atoi(c2) : 0;
       const char *c3 = getenv("MVTV_STEP2D_PREC_CFG");
       step2d_prec_cfg = c3 ? atoi(c3) : 0;
+      const char *e3 = getenv("MVTV_STEP3D");
+      step3d = e3 && std::string(e3) == "shfl" && P == 3 && (m[0] % 2 == 0) && m[0] >= 2;
+      const char *c4 = getenv("MVTV_STEP3D_CFG");
+      step3d_cfg = c4 ? atoi(c4) : 0;
     }
 
     // 3^P-point stencil of D^T D = sum_b c_b^2 kron_{a in S'_b} L_a  (SURVEY A.6), clamped indices
@@ -938,6 +945,32 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       gs_prec = chunking2((unsigned)((m0 + C2::TX - 1) / C2::TX), occ, zchunk_prec);
     });
   }
+  // 3-D meshes, opt-in: the shuffle-based kernel (cg_step3d.cuh); a warp owns 64 x RY vertices of a plane
+  const bool use3d = (P == 3) && step3d;
+  auto dispatch3d = [&](auto &&fn) {
+    switch (step3d_cfg) {
+      case 1: fn(Step3dCfg<4, 4>{}); break;
+      case 2: fn(Step3dCfg<8, 2>{}); break;
+      case 3: fn(Step3dCfg<4, 3>{}); break;
+      case 4: fn(Step3dCfg<8, 4>{}); break;
+      case 5: fn(Step3dCfg<4, 2, 0, false>{}); break;   // preconditioner reads diag(c)
+      case 6: fn(Step3dCfg<8, 1>{}); break;             // one row per warp: fewer registers, more warps, 3 rows loaded per row
+      case 7: fn(Step3dCfg<16, 1>{}); break;
+      default: fn(Step3dCfg<4, 2>{}); break;
+    }
+  };
+  if (use3d) {
+    dispatch3d([&](auto cfg) {
+      using C3 = decltype(cfg);
+      const unsigned tiles3 = (unsigned)(((m0 + C3::TX - 1) / C3::TX) * ((m1 + C3::TY - 1) / C3::TY));
+      int occ = 1, occp = 1;
+      if (prec) MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step3d<T, C3, STEP_Z>, C3::NT, 0));
+      else MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step3d<T, C3, STEP_JACOBI>, C3::NT, 0));
+      MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, k_cg_step3d<T, C3, STEP_PREC>, C3::NT, 0));
+      gs = chunking2(tiles3, occ, zchunk);
+      gs_prec = chunking2(tiles3, occp, zchunk_prec);
+    });
+  }
   const int gu = (int)std::max<long long>(1, std::min<long long>(148 * 8, (dt.Nloc + 1023) / 1024));
   int launched = 0;
   int batch = std::max(2, std::min(last_cg_iters, 256));
@@ -952,6 +985,10 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
         if (use2d) dispatch2d_prec([&](auto cfg) {
           using C2 = decltype(cfg);
           k_cg_step2d<T, C2, STEP_PREC><<<gs_prec, C2::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
+        });
+        else if (use3d) dispatch3d([&](auto cfg) {
+          using C3 = decltype(cfg);
+          k_cg_step3d<T, C3, STEP_PREC><<<gs_prec, C3::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
         });
         else k_cg_step<T, Cfg, STEP_PREC><<<gs_prec, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
         prof_end();
@@ -971,6 +1008,12 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
           using C2 = decltype(cfg);
           if (prec) k_cg_step2d<T, C2, STEP_Z><<<gs, C2::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
           else k_cg_step2d<T, C2, STEP_JACOBI><<<gs, C2::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+        });
+      } else if (use3d) {
+        dispatch3d([&](auto cfg) {
+          using C3 = decltype(cfg);
+          if (prec) k_cg_step3d<T, C3, STEP_Z><<<gs, C3::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+          else k_cg_step3d<T, C3, STEP_JACOBI><<<gs, C3::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
         });
       } else if (prec) k_cg_step<T, Cfg, STEP_Z><<<gs, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       else k_cg_step<T, Cfg, STEP_JACOBI><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
@@ -1400,12 +1443,14 @@ int mvtv_plan_describe(const mvtv_plan *plan, char *buf, int64_t cap) {
   return guarded([&] {
     MVTV_REQUIRE(plan && buf && cap > 0, "null argument");
     const bool s2 = plan->step2d && plan->dt.P == 2;
+    const bool s3 = plan->step3d && plan->dt.P == 3;
     char tmp[512];
     snprintf(tmp, sizeof(tmp),
              "{\"p\": %d, \"dtype\": %d, \"world\": %d, \"zu\": \"%s\", \"cg_step\": \"%s\", \"cg_prec\": \"%s\", "
              "\"cg_prec_words\": %d, \"collectives\": \"%s\"}",
              plan->p, plan->dtype, plan->world, plan->zu_variant >= 0 ? "k_zu_march" : "k_zu",
-             s2 ? "k_cg_step2d" : "k_cg_step", s2 ? "k_cg_step2d" : "k_cg_step", s2 ? 3 : 4,
+             s2 ? "k_cg_step2d" : (s3 ? "k_cg_step3d" : "k_cg_step"), s2 ? "k_cg_step2d" : (s3 ? "k_cg_step3d" : "k_cg_step"),
+             (s2 || (s3 && plan->step3d_cfg != 5)) ? 3 : 4,
              plan->world == 1 ? "none" : (plan->d_peer ? "peer" : "nccl"));
     MVTV_REQUIRE((int64_t)strlen(tmp) < cap, "buffer too small");
     strcpy(buf, tmp);

@@ -540,3 +540,22 @@ def test_step2d_kernel_cross_check(mv, monkeypatch):
         assert d["cg_step"] == "k_cg_step2d" and d["cg_prec_words"] == 3 and d["collectives"] == "none"
     with mv.Plan([8, 8, 8]) as pl:
         assert pl.describe()["cg_step"] == "k_cg_step"
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MVTV_EXPERIMENTAL") != "1",
+                    reason="k_cg_step3d is opt-in (MVTV_STEP3D=shfl) and not yet validated on a GPU: set MVTV_EXPERIMENTAL=1")
+def test_step3d_kernel_cross_check_experimental(mv, monkeypatch):
+    """EXPERIMENTAL k_cg_step3d (cg_step3d.cuh) vs k_cg_step on 3-D meshes; see tools/step3d_probe.py."""
+    for dims, n in ([12, 12, 12], 2000), ([66, 5, 7], 1500), ([130, 33, 6], 9000):
+        x, y = synth(90 + dims[0], n, 3, 0.0, 1.0, 0.5)
+        axes = po.mesh_axes(x, dims, po.MODE_RCPP)
+        res = {}
+        for which in ("shfl", "smem"):
+            monkeypatch.setenv("MVTV_STEP3D", which)
+            with mv.Plan(dims) as pl:
+                assert pl.describe()["cg_step"] == ("k_cg_step3d" if which == "shfl" else "k_cg_step")
+                pl.set_points(x, y, axes)
+                res[which] = pl.solve(0.8, mode="rcpp", max_passes=30, precond=mv.PRECOND_CHEB1)
+        monkeypatch.delenv("MVTV_STEP3D", raising=False)
+        assert res["shfl"]["passes"] == res["smem"]["passes"]
+        assert np.abs(res["shfl"]["theta"] - res["smem"]["theta"]).max() <= 1e-10
