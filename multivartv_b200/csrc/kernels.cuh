@@ -12,6 +12,11 @@
 #pragma once
 #include "mvtv_internal.cuh"
 
+// dynamic shared memory of a kernel (the CPU emulator of tests/cuda_emu hands out one host buffer instead)
+#ifndef MVTV_DYN_SMEM
+#define MVTV_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace mvtv {
 
 // slots of the ADMM reduction
@@ -220,6 +225,12 @@ struct PeerTab {
   int *error;                                 // set when a wait times out (a peer died): results become NaN
 };
 
+#ifdef MVTV_CUDA_EMU   // tests/cuda_emu: the kernel source compiled for the CPU emulator (one thread at a time: plain accesses)
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { *p = v; }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) { return *p; }
+__device__ __forceinline__ void st_relaxed_sys(double *p, double v) { *p = v; }
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) { return *p; }
+#else
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -236,6 +247,7 @@ __device__ __forceinline__ double ld_relaxed_sys(const double *p) {
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
+#endif
 // returns false on timeout (~10 s): never hang the GPU on a dead peer
 __device__ __forceinline__ bool peer_spin(const unsigned long long *flag, unsigned long long seq, int *error) {
   const long long t0 = clock64();
@@ -440,6 +452,13 @@ struct StepCfg {
   static_assert(Q_ >= 3 || TW_ == 1, "Q<3 has no axis 2");
 };
 
+#ifdef MVTV_CUDA_EMU   // CPU emulator: the copy completes at once, groups are no-ops
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, BYTES); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -448,6 +467,7 @@ __device__ __forceinline__ void cp_async(void *smem_dst, const void *gmem_src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+#endif
 
 // MODE: what the staged arrays are and what leaves the kernel
 //   STEP_JACOBI  stage r, dinv, p_old : p = dinv.*r + beta*p_old ; writes p, q = M p ; reduces p.q
@@ -464,7 +484,7 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   constexpr int NT = Cfg::NT, EX = Cfg::EX, EY = Cfg::EY, TE = Cfg::TE, NE = Cfg::NE, DEPTH = Cfg::DEPTH;
   constexpr int NDY = (Q >= 2) ? 3 : 1, NDW = (Q >= 3) ? 3 : 1;   // in-plane stencil extents beyond axis 0
   constexpr int PW = 3 * NDY * NDW;                                 // stencil points per plane
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MVTV_DYN_SMEM(smem_raw);
   constexpr int NARR = Cfg::template narr<MODE>();     // staged arrays per plane (ring stride)
   constexpr int SLOT_B = 1;                              // dinv (JACOBI, PREC)
   constexpr int SLOT_C = (MODE == STEP_Z && NARR == 2) ? 1 : 2;  // p_old (JACOBI, Z)

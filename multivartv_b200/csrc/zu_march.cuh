@@ -81,7 +81,7 @@ k_zu_march(const __grid_constant__ DimTab dt, const __grid_constant__ BlockTab b
   constexpr int OX = Cfg::OX, OY = Cfg::OY, OW = Cfg::OW, SX = Cfg::SX, SY = Cfg::SY, ST = Cfg::ST, NS = Cfg::NS;
   constexpr int NF = Cfg::NF, K = zu_num_blocks(P, V);
   constexpr int ZBIT = 1 << Q;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MVTV_DYN_SMEM(smem_raw);
   T *sth = reinterpret_cast<T *>(smem_raw);  // [3][ST] theta planes zz, zz+1 and (in flight) zz+2; slot = plane % 3
   T *sh = sth + 3 * ST;                      // [(NF-1)][3][NT] in-plane exchange
 

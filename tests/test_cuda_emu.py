@@ -1,0 +1,28 @@
+"""The library's CUDA kernel SOURCE run on a CPU SIMT emulator (tests/cuda_emu/cuda_emu.h: one ucontext fiber per CUDA thread,
+barriers for __syncthreads and warp shuffles): logic checks that need no GPU.  tests/cuda_emu/emu_cg_step.cpp compares
+k_cg_step, k_cg_step2d and the not-yet-GPU-run k_cg_step3d with a host loop over the clamped stencil, single rank and slab
+by slab.  CPU test; says nothing about performance or PTX-level behaviour."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "cuda_emu")
+
+
+def _build(tmp_path):
+    exe = str(tmp_path / "emu_cg_step")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([gxx, "-std=c++17", "-O1", "-w", "-I", os.path.join(EMU, "fake"), "-I", EMU,
+                           os.path.join(EMU, "emu_cg_step.cpp"), "-o", exe])
+    return exe
+
+
+def test_cg_step_kernels_on_the_emulator(tmp_path):
+    exe = _build(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "emu_cg_step: 0 failure(s)" in r.stdout
+    # self-test of the comparisons: a 1e-6 perturbation of the kernels' matrix scalar must be caught
+    env = dict(os.environ, EMU_NEGATIVE="1")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 1 and "FAIL" in r.stdout
