@@ -14,6 +14,8 @@
 //
 // Algorithmic traffic: as k_cg_step (JACOBI 6 N, Z 5 N, PREC 4 N words).
 #pragma once
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace mvtv {
@@ -40,10 +42,12 @@ __device__ __forceinline__ void st2(T *__restrict__ p, T a, T b) {
 // row), MINB = minimum resident CTAs per SM asked of the compiler (0: none), NOC: STEP_PREC derives diag(c) from dinv
 // instead of reading it (dinv*c = 1 - dinv*rhoM*diag(K)), i.e. 3 N words instead of 4 N.
 // DKSEL: NOC picks diag(K) of a vertex with selects on constant-bank operands instead of holding 2*VPL values in registers.
-template <int WARPS_, int PF_, int VPL_ = 2, int MINB_ = 0, bool NOC_ = false, bool DKSEL_ = false>
+// IDX32: element offsets inside the ghosted slab in 32 bits (a slab holds < 2^31 vertices, enforced at plan creation; the
+// two ghost planes keep the largest offset below 2^32), which saves the registers of the 64-bit index arithmetic.
+template <int WARPS_, int PF_, int VPL_ = 2, int MINB_ = 0, bool NOC_ = false, bool DKSEL_ = false, bool IDX32_ = false>
 struct Step2dCfg {
   static constexpr int WARPS = WARPS_, PF = PF_, VPL = VPL_, NG = VPL_ / 2, MINB = MINB_;
-  static constexpr bool NOC = NOC_, DKSEL = DKSEL_;
+  static constexpr bool NOC = NOC_, DKSEL = DKSEL_, IDX32 = IDX32_;
   static constexpr int NT = 32 * WARPS_, SW = 32 * VPL_, TX = SW * WARPS_;
   static_assert(VPL_ == 2 || VPL_ == 4, "two or four vertices per lane");
 };
@@ -55,6 +59,8 @@ k_cg_step2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   if (cg_done(a.S, a.rtol2)) return;
   constexpr int PF = Cfg::PF, VPL = Cfg::VPL, NG = Cfg::NG, SW = Cfg::SW;
   constexpr bool NOC = Cfg::NOC && (MODE == STEP_PREC);
+  using idx_t = typename std::conditional<Cfg::IDX32, unsigned, long long>::type;
+  const idx_t plane = (idx_t)dt.plane;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int it = (int)a.S[CS_ITERS];
   const int cur = it & 1;
@@ -118,22 +124,22 @@ k_cg_step2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   auto load_row = [&](int zz, int s) {
     if (zz > zlast) return;
     const int zs = min(max(zz, zlo), zhi);
-    const long long pb = (long long)(zs + 1) * dt.plane;
+    const idx_t pb = (idx_t)(zs + 1) * plane;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      ld2(rr + pb + xo[g], *reinterpret_cast<T(*)[2]>(&ra[s][2 * g]));
-      if (MODE != STEP_Z) ld2(dinv + pb + xo[g], *reinterpret_cast<T(*)[2]>(&rb_[s][2 * g]));
-      if (!first) ld2(p_in + pb + xo[g], *reinterpret_cast<T(*)[2]>(&rc[s][2 * g]));
+      ld2(rr + (pb + (idx_t)xo[g]), *reinterpret_cast<T(*)[2]>(&ra[s][2 * g]));
+      if (MODE != STEP_Z) ld2(dinv + (pb + (idx_t)xo[g]), *reinterpret_cast<T(*)[2]>(&rb_[s][2 * g]));
+      if (!first) ld2(p_in + (pb + (idx_t)xo[g]), *reinterpret_cast<T(*)[2]>(&rc[s][2 * g]));
     }
     if (edge) {
-      ha[s] = rr[pb + xh];
-      if (MODE != STEP_Z) hb[s] = dinv[pb + xh];
-      if (!first) hc[s] = p_in[pb + xh];
+      ha[s] = rr[pb + (idx_t)xh];
+      if (MODE != STEP_Z) hb[s] = dinv[pb + (idx_t)xh];
+      if (!first) hc[s] = p_in[pb + (idx_t)xh];
     }
     if (!NOC && zz >= zc0 && zz < zc1) {
 #pragma unroll
       for (int g = 0; g < NG; ++g)
-        if (valid[g]) ld2(a.c + (long long)(zz + 1) * dt.plane + x + 2 * g, *reinterpret_cast<T(*)[2]>(&rcc[s][2 * g]));
+        if (valid[g]) ld2(a.c + ((idx_t)(zz + 1) * plane + (idx_t)(x + 2 * g)), *reinterpret_cast<T(*)[2]>(&rcc[s][2 * g]));
     }
   };
 
@@ -171,7 +177,7 @@ k_cg_step2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
           if (MODE != STEP_PREC && own) {
 #pragma unroll
             for (int g = 0; g < NG; ++g)
-              if (valid[g]) st2(p_out + (long long)(zs + 1) * dt.plane + x + 2 * g, v[2 * g], v[2 * g + 1]);
+              if (valid[g]) st2(p_out + ((idx_t)(zs + 1) * plane + (idx_t)(x + 2 * g)), v[2 * g], v[2 * g + 1]);
           }
         }
         // ---- neighbours along axis 0 from the adjacent lanes
@@ -192,7 +198,7 @@ k_cg_step2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
         }
         // ---- retire output row zz-1
         if (zz - 1 >= zc0) {
-          const long long ob = (long long)zz * dt.plane + x;   // local row zz-1 sits at (zz-1+1)*plane
+          const idx_t ob = (idx_t)zz * plane + (idx_t)x;       // local row zz-1 sits at (zz-1+1)*plane
           const long long gz = dt.z0 + zz - 1;
           const bool bz = (gz == 0 || gz == dt.m[1] - 1);
           T outv[VPL];

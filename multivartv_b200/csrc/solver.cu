@@ -909,6 +909,9 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       case 6: fn(Step2dCfg<8, 1, 2, 4, true, true>{}); break;
       case 7: fn(Step2dCfg<8, 1, 2, 3, true, true>{}); break;
       case 8: fn(Step2dCfg<8, 1, 2, 3, true, false>{}); break;
+      case 9: fn(Step2dCfg<8, 1, 2, 4, true, false, true>{}); break;    // 32-bit in-slab offsets
+      case 10: fn(Step2dCfg<8, 1, 2, 4, true, true, true>{}); break;
+      case 11: fn(Step2dCfg<8, 1, 2, 5, true, true, true>{}); break;    // <= 51 registers, 40 warps per SM
       default: fn(Step2dCfg<8, 1, 2, 4, true>{}); break;
     }
   };

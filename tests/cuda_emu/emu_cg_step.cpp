@@ -304,6 +304,8 @@ static void check_2d(std::vector<long long> m, const std::vector<double> &deltas
     one(Step2dCfg<4, 1, 4, 0>{}, "k_cg_step2d<4,1,4>");
     one(Step2dCfg<8, 1, 2, 4, true>{}, "k_cg_step2d<8,1,2,noc>");
     one(Step2dCfg<4, 2, 2, 0>{}, "k_cg_step2d<4,2,2>");
+    one(Step2dCfg<8, 1, 2, 4, true, true, true>{}, "k_cg_step2d<8,1,2,noc,dksel,idx32>");
+    one(Step2dCfg<8, 1, 2, 4, false, false, true>{}, "k_cg_step2d<8,1,2,c,idx32>");
   }
 }
 

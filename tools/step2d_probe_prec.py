@@ -9,7 +9,7 @@ import multivartv_b200 as mv  # noqa: E402
 from bench import synth_points  # noqa: E402
 from step2d_probe import run  # noqa: E402,F401  (module-level probe code is guarded below)
 
-CFGS = (0, 6, 7, 8)
+CFGS = (0, 6, 9, 10, 11)
 for m, n in (([100, 37], 3000), ([258, 33], 9000)):
     x, y = synth_points(n, 2, 5)
     axes = [np.linspace(0.0, 1.0, d) for d in m]
