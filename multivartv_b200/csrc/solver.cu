@@ -153,6 +153,7 @@ struct mvtv_plan {
   bool step3d = false;   // 3-D meshes: EXPERIMENTAL shuffle-based k_cg_step3d (MVTV_STEP3D=shfl), default off
   int step3d_cfg = 0;
   bool step2d = false;   // 2-D meshes: shuffle-based k_cg_step2d (cg_step2d.cuh) instead of the shared-memory k_cg_step
+  int zu_cfg = 0;        // tile variant of k_zu_march (MVTV_ZU_CFG), 0 = default
   int zu_variant = -1;   // ZV_* when the compile-time block tables of k_zu_march match this plan, else -1 (gather kernel)
 
   // optional per-kernel-class CUDA-event timing on the plan's stream (mvtv_plan_profile)
@@ -326,6 +327,8 @@ struct mvtv_plan {
       for (int b = 0; same && b < K; ++b) same = (zu_block_mask(P, V, b) == bt.mask[b]);
       const char *env = getenv("MVTV_ZU_KERNEL");
       zu_variant = (same && !(env && std::string(env) == "gather")) ? V : -1;
+      const char *zc = getenv("MVTV_ZU_CFG");
+      zu_cfg = zc ? atoi(zc) : 0;
     }
 
     {
@@ -761,9 +764,27 @@ void mvtv_plan::launch_zu(double kappa, double usc, int mode, int init, bool wit
       case 2 * 4 + ZV_REFERENCE: launch_zu_march<T, ZuCfg<2, 256, 1, 1>, ZV_REFERENCE>(a, rb); done = true; break;
       case 2 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<2, 256, 1, 1>, ZV_INTENDED>(a, rb); done = true; break;
       case 2 * 4 + ZV_P1: launch_zu_march<T, ZuCfg<2, 256, 1, 1>, ZV_P1>(a, rb); done = true; break;
-      case 3 * 4 + ZV_REFERENCE: launch_zu_march<T, ZuCfg<3, 32, 16, 1>, ZV_REFERENCE>(a, rb); done = true; break;
+      case 3 * 4 + ZV_REFERENCE:
+        switch (zu_cfg) {   // tile variants for the occupancy / halo-overhead sweep (MVTV_ZU_CFG); 0 = the measured default
+          case 1: launch_zu_march<T, ZuCfg<3, 32, 8, 1>, ZV_REFERENCE>(a, rb); break;    // 256 threads
+          case 2: launch_zu_march<T, ZuCfg<3, 64, 8, 1>, ZV_REFERENCE>(a, rb); break;    // 512 threads, less x halo
+          case 3: launch_zu_march<T, ZuCfg<3, 64, 4, 1>, ZV_REFERENCE>(a, rb); break;    // 256 threads
+          case 4: launch_zu_march<T, ZuCfg<3, 16, 16, 1>, ZV_REFERENCE>(a, rb); break;   // 256 threads
+          default: launch_zu_march<T, ZuCfg<3, 32, 16, 1>, ZV_REFERENCE>(a, rb); break;
+        }
+        done = true;
+        break;
       case 3 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<3, 32, 16, 1>, ZV_INTENDED>(a, rb); done = true; break;
-      case 4 * 4 + ZV_REFERENCE: launch_zu_march<T, ZuCfg<4, 16, 8, 4>, ZV_REFERENCE>(a, rb); done = true; break;
+      case 4 * 4 + ZV_REFERENCE:
+        switch (zu_cfg) {
+          case 1: launch_zu_march<T, ZuCfg<4, 16, 4, 4>, ZV_REFERENCE>(a, rb); break;    // 256 threads: no register spills
+          case 2: launch_zu_march<T, ZuCfg<4, 8, 8, 4>, ZV_REFERENCE>(a, rb); break;     // 256 threads
+          case 3: launch_zu_march<T, ZuCfg<4, 8, 8, 8>, ZV_REFERENCE>(a, rb); break;     // 512 threads, cubic tile
+          case 4: launch_zu_march<T, ZuCfg<4, 16, 8, 2>, ZV_REFERENCE>(a, rb); break;    // 256 threads
+          default: launch_zu_march<T, ZuCfg<4, 16, 8, 4>, ZV_REFERENCE>(a, rb); break;
+        }
+        done = true;
+        break;
       case 4 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<4, 16, 8, 4>, ZV_INTENDED>(a, rb); done = true; break;
       default: break;
     }

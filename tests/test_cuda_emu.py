@@ -9,12 +9,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "cuda_emu")
 
 
-def _build(tmp_path):
-    exe = str(tmp_path / "emu_cg_step")
+def _build(tmp_path, name="emu_cg_step"):
+    exe = str(tmp_path / name)
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     subprocess.check_call([gxx, "-std=c++17", "-O1", "-w", "-I", os.path.join(EMU, "fake"), "-I", EMU,
-                           os.path.join(EMU, "emu_cg_step.cpp"), "-o", exe])
+                           os.path.join(EMU, name + ".cpp"), "-o", exe])
     return exe
+
+
+def test_zu_kernels_on_the_emulator(tmp_path):
+    """k_zu (gather) vs k_zu_march (scatter, marching) in every tile variant solver.cu can select (MVTV_ZU_CFG), 2-D / 3-D / 4-D."""
+    exe = _build(tmp_path, "emu_zu")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "emu_zu: 0 failure(s)" in r.stdout
 
 
 def test_cg_step_kernels_on_the_emulator(tmp_path):
