@@ -384,7 +384,7 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": launches, "roofline": roof, "stages": stages, "e2e": e2e,
     }
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_baseline(args, threads=0, passes=2)
+        cb = cpu_baseline(args, threads=0, passes=12, warm=1)   # ~5-10 s of CPU work on the box's 16 host threads
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if dist:
