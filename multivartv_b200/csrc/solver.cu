@@ -16,6 +16,7 @@
 
 #include "cg_step2d.cuh"
 #include "cg_step3d.cuh"
+#include "cg_fused2d.cuh"
 #include "kernels.cuh"
 #include "setup.h"
 #include "zu_march.cuh"
@@ -150,6 +151,9 @@ struct mvtv_plan {
   unsigned long long red_seq = 0, halo_seq = 0, zhalo_seq = 0;
   double cheb_bmax = 0.0;   // bound on the spectrum of D^-1 (diag(c) + s D^T D), independent of s and c
   int step2d_cfg = 0, step2d_prec_cfg = 0;   // tile variants of k_cg_step2d (MVTV_STEP2D_CFG, MVTV_STEP2D_PREC_CFG)
+  bool fuse_updprec = false;   // 2-D, one GPU: EXPERIMENTAL k_cg_updprec2d (MVTV_FUSE_UPDPREC=1), default off
+  int fuse_cfg = 0;
+  void *r2 = nullptr;          // second residual buffer of the fused kernel (allocated on first use)
   bool step3d = false;   // 3-D meshes: EXPERIMENTAL shuffle-based k_cg_step3d (MVTV_STEP3D=shfl), default off
   int step3d_cfg = 0;
   bool step2d = false;   // 2-D meshes: shuffle-based k_cg_step2d (cg_step2d.cuh) instead of the shared-memory k_cg_step
@@ -232,7 +236,7 @@ struct mvtv_plan {
     if (cb) cudaFree(cb);
     if (d_peer) cudaFree(d_peer);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pbuf[0], pbuf[1], q, dinv, zbuf, u[0], u[1], S, zr, raw, partials, counters, vid, staging, in_buf, sort_buf};
+    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pbuf[0], pbuf[1], q, dinv, zbuf, u[0], u[1], S, zr, raw, partials, counters, vid, staging, in_buf, sort_buf, r2};
     for (void *b : bufs)
       if (b) cudaFree(b);
     if (h_scal) cudaFreeHost(h_scal);
@@ -339,6 +343,10 @@ struct mvtv_plan {
       step2d_cfg = c2 ? atoi(c2) : 0;
       const char *c3 = getenv("MVTV_STEP2D_PREC_CFG");
       step2d_prec_cfg = c3 ? atoi(c3) : 0;
+      const char *ef = getenv("MVTV_FUSE_UPDPREC");
+      fuse_updprec = ef && std::string(ef) == "1" && step2d && world == 1;
+      const char *cf = getenv("MVTV_FUSE_CFG");
+      fuse_cfg = cf ? atoi(cf) : 0;
       const char *e3 = getenv("MVTV_STEP3D");
       step3d = e3 && std::string(e3) == "shfl" && P == 3 && (m[0] % 2 == 0) && m[0] >= 2;
       const char *c4 = getenv("MVTV_STEP3D_CFG");
@@ -996,13 +1004,39 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     });
   }
   const int gu = (int)std::max<long long>(1, std::min<long long>(148 * 8, (dt.Nloc + 1023) / 1024));
+  // 2-D, one GPU, polynomial preconditioner, opt-in: vector update fused with the preconditioner (cg_fused2d.cuh)
+  const bool fused = use2d && prec && world == 1 && fuse_updprec;
+  dim3 gs_fused = gs_prec;
+  int zchunk_fused = zchunk_prec;
+  auto dispatch_fused = [&](auto &&fn) {
+    switch (fuse_cfg) {
+      case 1: fn(Fused2dCfg<8, 3>{}); break;   // <= 85 registers
+      case 2: fn(Fused2dCfg<4, 0>{}); break;
+      case 3: fn(Fused2dCfg<8, 4>{}); break;   // <= 64 registers
+      default: fn(Fused2dCfg<8, 0>{}); break;
+    }
+  };
+  if (fused) {
+    if (!r2) {
+      MVTV_CUDA(cudaMalloc(&r2, (size_t)dt.usz * esz()));
+      MVTV_CUDA(cudaMemsetAsync(r2, 0, (size_t)dt.usz * esz(), stream));
+    }
+    dispatch_fused([&](auto cfg) {
+      using CF = decltype(cfg);
+      int occ = 1;
+      MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_updprec2d<T, CF>, CF::NT, 0));
+      gs_fused = chunking2((unsigned)((m0 + CF::TX - 1) / CF::TX), occ, zchunk_fused);
+    });
+  }
+  bool first_prec_done = false;
   int launched = 0;
   int batch = std::max(2, std::min(last_cg_iters, 256));
   double iters = 0;
   for (;;) {
     for (int k = 0; k < batch; ++k) {
       if (world > 1 && !d_peer) exchange_ghosts<T>((T *)r);
-      if (prec) {  // z = P(D^-1 M) D^-1 r and r.z
+      if (prec && !(fused && first_prec_done)) {  // z = P(D^-1 M) D^-1 r and r.z (fused path: only before the first iteration)
+        first_prec_done = true;
         a.seq_red = ++red_seq;
         a.seq_zhalo = ++zhalo_seq;
         prof_begin(MVTV_KC_CG_PREC);
@@ -1051,7 +1085,11 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       a.seq_red = ++red_seq;
       a.seq_halo = ++halo_seq;
       prof_begin(MVTV_KC_CG_UPDATE);
-      k_cg_update<T><<<gu, 256, 0, stream>>>(a, dt.plane, dt.Nloc, RedBuf{partials, counters + 3});
+      if (fused) dispatch_fused([&](auto cfg) {
+        using CF = decltype(cfg);
+        k_cg_updprec2d<T, CF><<<gs_fused, CF::NT, 0, stream>>>(dt, st, a, (T *)r, (T *)r2, RedBuf{partials, counters + 3}, zchunk_fused);
+      });
+      else k_cg_update<T><<<gu, 256, 0, stream>>>(a, dt.plane, dt.Nloc, RedBuf{partials, counters + 3});
       prof_end();
       if (d_peer) {
         if (prec) k_cg_peer_commit_update_prec<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);

@@ -17,6 +17,7 @@
 #include "../../multivartv_b200/csrc/zu_march.cuh"
 #include "../../multivartv_b200/csrc/cg_step2d.cuh"
 #include "../../multivartv_b200/csrc/cg_step3d.cuh"
+#include "../../multivartv_b200/csrc/cg_fused2d.cuh"
 // clang-format on
 
 using namespace mvtv;
@@ -410,6 +411,69 @@ static void check_slabs_all(unsigned seed) {
   }
 }
 
+
+// ---- k_cg_updprec2d (vector update fused with the preconditioner): against x + a p, r - a q, P(D^-1 M) D^-1 r_new on the host
+template <typename CF>
+static void check_fused(const char *name, std::vector<long long> m, const std::vector<double> &deltas, unsigned seed, int iters) {
+  Problem pb = make_problem(m, deltas, seed);
+  const DimTab dt = pb.M.dt;
+  const StencilTab st = pb.M.st;
+  std::mt19937_64 g(seed + 100);
+  std::normal_distribution<double> nd(0.0, 1.0);
+  std::vector<double> q((size_t)dt.usz, 0.0);
+  for (long long i = dt.plane; i < dt.plane + dt.Nloc; ++i) q[(size_t)i] = nd(g);
+  const double rz = 0.9, pq = 1.7, alpha = rz / pq;
+  // host reference
+  Problem pr = pb;
+  std::vector<double> x_ref = pb.x, r_ref = pb.r;
+  double rr_ref = 0.0;
+  for (long long i = dt.plane; i < dt.plane + dt.Nloc; ++i) {
+    x_ref[(size_t)i] = pb.x[(size_t)i] + alpha * pb.p_in[(size_t)i];
+    r_ref[(size_t)i] = pb.r[(size_t)i] - alpha * q[(size_t)i];
+    rr_ref += r_ref[(size_t)i] * r_ref[(size_t)i];
+  }
+  pr.r = r_ref;
+  Out ref;
+  host_reference(pr, STEP_PREC, ref);   // z = P r_new, scalar = r_new . z
+  // kernel
+  const int cur = iters & 1;
+  std::vector<double> x = pb.x, p = pb.p_in, r0 = pb.r, r1 = pb.r, dinv = pb.dinv, z((size_t)dt.usz, 0.0), S(CS_N, 0.0);
+  std::vector<double> &r_in = cur ? r1 : r0, &r_out = cur ? r0 : r1;
+  std::fill(r_out.begin(), r_out.end(), -777.0);   // stale contents of the other buffer must not matter
+  (void)r_in;
+  S[CS_ITERS] = (double)iters;
+  S[2 * cur] = rz; S[2 * cur + 1] = 1.0; S[2 * (cur ^ 1)] = 0.3; S[2 * (cur ^ 1) + 1] = 2.0;
+  S[CS_PQ] = pq; S[CS_BB] = 1.0;
+  CgArgs<double> a{};
+  a.x = x.data(); a.q = q.data(); a.pbuf[cur ^ 1] = p.data(); a.pbuf[cur] = nullptr; a.dinv = dinv.data(); a.S = S.data();
+  a.rhoM = pb.rhoM; a.rtol2 = 1e-26; a.z = z.data(); a.pc0 = pb.pc0; a.pc1 = pb.pc1; a.prec = 1;
+  std::vector<double> partials(1 << 16, 0.0);
+  unsigned counter = 0;
+  for (int nchunk = 1; nchunk <= 2; ++nchunk) {
+    std::vector<double> xs = x, r0s = r0, r1s = r1, zs = z, Ss = S;
+    a.x = xs.data(); a.z = zs.data(); a.S = Ss.data();
+    const int zchunk = (dt.nz + nchunk - 1) / nchunk;
+    const unsigned tiles = (unsigned)((dt.m[0] + CF::TX - 1) / CF::TX);
+    cuda_emu::launch(dim3(tiles, (unsigned)((dt.nz + zchunk - 1) / zchunk), 1), dim3(CF::NT, 1, 1), 0,
+                     [&] { k_cg_updprec2d<double, CF>(dt, st, a, r0s.data(), r1s.data(), RedBuf{partials.data(), &counter}, zchunk); });
+    const std::vector<double> &rn = cur ? r0s : r1s;
+    double ex = 0, er = 0, ez = 0;
+    for (long long i = dt.plane; i < dt.plane + dt.Nloc; ++i) {
+      ex = std::max(ex, std::fabs(xs[(size_t)i] - x_ref[(size_t)i]));
+      er = std::max(er, std::fabs(rn[(size_t)i] - r_ref[(size_t)i]));
+      ez = std::max(ez, std::fabs(zs[(size_t)i] - ref.z[(size_t)i]));
+    }
+    const int nxt = cur ^ 1;
+    const double es = std::max(std::fabs(Ss[2 * nxt] - ref.scalar) / std::max(1.0, std::fabs(ref.scalar)),
+                               std::fabs(Ss[2 * nxt + 1] - rr_ref) / std::max(1.0, rr_ref));
+    if (!(ex <= 1e-13 && er <= 1e-13 && ez <= 1e-12 && es <= 1e-12 && Ss[CS_ITERS] == iters + 1.0)) {
+      ++g_fail;
+      std::printf("FAIL fused %s mesh=%lldx%lld iters=%d chunks=%d: x %.2e r %.2e z %.2e scalars %.2e iters %g\n", name, dt.m[0], dt.m[1], iters, nchunk,
+                  ex, er, ez, es, Ss[CS_ITERS]);
+    }
+  }
+}
+
 int main() {
   const std::vector<double> none, d2 = {0.5, 0.25}, d3 = {0.3, 0.5, 2.0};
   // 2-D: the GPU-validated pair first (this validates the emulator itself)
@@ -426,6 +490,11 @@ int main() {
     check_3d<STEP_PREC>(m, none, 6);
     check_3d<STEP_PREC>(m, d3, 7);
   }
+  for (auto m : std::vector<std::vector<long long>>{{66, 5}, {130, 9}, {2, 7}, {258, 4}, {64, 12}})
+    for (int iters : {0, 1, 4}) {
+      check_fused<Fused2dCfg<8, 0>>("<8>", m, none, 21 + (unsigned)iters, iters);
+      check_fused<Fused2dCfg<4, 0>>("<4>", m, d2, 31 + (unsigned)iters, iters);
+    }
   check_slabs_all<STEP_JACOBI>(11);
   check_slabs_all<STEP_Z>(12);
   check_slabs_all<STEP_PREC>(13);

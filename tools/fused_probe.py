@@ -1,0 +1,54 @@
+"""Probe (round 2): the EXPERIMENTAL fused vector-update + preconditioner kernel k_cg_updprec2d (MVTV_FUSE_UPDPREC=1) against
+the separate k_cg_update + k_cg_step2d<STEP_PREC> on 2-D meshes: parity on awkward shapes, then ms/pass on 4096^2.
+
+    python tools/fused_probe.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import multivartv_b200 as mv  # noqa: E402
+from bench import synth_points  # noqa: E402
+
+
+def run(m, x, y, axes, env, passes):
+    for k in ("MVTV_FUSE_UPDPREC", "MVTV_FUSE_CFG"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    with mv.Plan(m) as plan:
+        plan.set_points(x, y, axes)
+        kw = dict(mode="rcpp", cg_rtol=1e-13, want_fitted=False, raise_on_nonconvergence=False, precond=mv.PRECOND_CHEB1)
+        rw = plan.solve(1.0, max_passes=3, want_theta=False, **kw)
+        plan.profile(True)
+        r = plan.solve(1.0, max_passes=passes, flags=mv.WARM_THETA_FROM_PLAN | mv.WARM_U_FROM_PLAN, rho_init=rw["rho"],
+                       rho_matrix0=rw["rho"], **kw)
+        prof = plan.get_profile()
+    return r, prof
+
+
+def main():
+    for m, n in (([100, 37], 3000), ([66, 5], 400), ([2, 9], 60), ([258, 33], 9000)):
+        x, y = synth_points(n, 2, 5)
+        axes = [np.linspace(0.0, 1.0, d) for d in m]
+        ref, _ = run(m, x, y, axes, {}, 12)
+        for cfg in range(4):
+            got, _ = run(m, x, y, axes, {"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": str(cfg)}, 12)
+            err = float(np.abs(got["theta"] - ref["theta"]).max())
+            print("parity m=%s cfg=%d: max|dtheta|=%.2e passes %d vs %d inner %d vs %d %s" % (
+                m, cfg, err, got["passes"], ref["passes"], got["inner_iters"], ref["inner_iters"],
+                "ok" if err <= 1e-10 and got["passes"] == ref["passes"] else "MISMATCH"), flush=True)
+    m, n = [4096, 4096], 1 << 24
+    x, y = synth_points(n, 2, 117)
+    axes = [np.linspace(0.0, 1.0, d) for d in m]
+    for name, env in [("separate", {})] + [("fused%d" % c, {"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": str(c)}) for c in range(4)]:
+        r, prof = run(m, x, y, axes, env, 10)
+        inner = r["inner_iters"]
+        print("time %-9s ms/pass=%.3f inner/pass=%.1f  us/launch: step=%.1f update(+prec)=%.1f prec=%.1f" % (
+            name, 1e3 * r["device_seconds"] / r["passes"], inner / r["passes"], 1e3 * prof["cg_step"][0] / inner,
+            1e3 * prof["cg_update"][0] / inner, 1e3 * prof["cg_prec"][0] / max(1, prof["cg_prec"][1])), flush=True)
+
+
+if __name__ == "__main__":
+    main()
