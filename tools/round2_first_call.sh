@@ -1,0 +1,11 @@
+#!/bin/bash
+# First GPU call of the next round: time (and parity-check) everything that was written after round 1's GPU minutes ran out.
+# All of it is opt-in and logic-checked on the CPU emulator (tests/cuda_emu); nothing here changes a default.
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/round2_first_call.sh'
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 240 python tools/step3d_probe.py --big      > $OUT/r2_step3d_probe.log 2>&1; echo "step3d rc=$?"; grep -c " ok$" $OUT/r2_step3d_probe.log; grep "^time\|MISMATCH\|mismatches" $OUT/r2_step3d_probe.log | tail -24
+timeout 200 python tools/zu_probe.py --big          > $OUT/r2_zu_probe.log 2>&1;     echo "zu rc=$?";     tail -12 $OUT/r2_zu_probe.log
+timeout 120 python tools/fused_probe.py             > $OUT/r2_fused_probe.log 2>&1;  echo "fused rc=$?";  grep "^time\|MISMATCH" $OUT/r2_fused_probe.log
+timeout 60 python tools/step2d_probe_prec.py        > $OUT/r2_prec_probe.log 2>&1;   echo "prec rc=$?";   grep "^time\|MISMATCH" $OUT/r2_prec_probe.log
+MVTV_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "step3d or step2d" > $OUT/r2_pytest_experimental.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/r2_pytest_experimental.log
