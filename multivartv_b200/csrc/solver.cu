@@ -17,6 +17,7 @@
 #include "cg_step2d.cuh"
 #include "cg_step3d.cuh"
 #include "cg_fused2d.cuh"
+#include "cg_init2d.cuh"
 #include "kernels.cuh"
 #include "setup.h"
 #include "zu_march.cuh"
@@ -151,6 +152,7 @@ struct mvtv_plan {
   unsigned long long red_seq = 0, halo_seq = 0, zhalo_seq = 0;
   double cheb_bmax = 0.0;   // bound on the spectrum of D^-1 (diag(c) + s D^T D), independent of s and c
   int step2d_cfg = 0, step2d_prec_cfg = 0;   // tile variants of k_cg_step2d (MVTV_STEP2D_CFG, MVTV_STEP2D_PREC_CFG)
+  bool init2d = false;         // 2-D: EXPERIMENTAL marching k_cg_init2d (MVTV_INIT2D=1), default off
   bool fuse_updprec = false;   // 2-D, one GPU: EXPERIMENTAL k_cg_updprec2d (MVTV_FUSE_UPDPREC=1), default off
   int fuse_cfg = 0;
   void *r2 = nullptr;          // second residual buffer of the fused kernel (allocated on first use)
@@ -343,6 +345,8 @@ struct mvtv_plan {
       step2d_cfg = c2 ? atoi(c2) : 0;
       const char *c3 = getenv("MVTV_STEP2D_PREC_CFG");
       step2d_prec_cfg = c3 ? atoi(c3) : 0;
+      const char *ei = getenv("MVTV_INIT2D");
+      init2d = ei && std::string(ei) == "1" && step2d;
       const char *ef = getenv("MVTV_FUSE_UPDPREC");
       fuse_updprec = ef && std::string(ef) == "1" && step2d && world == 1;
       const char *cf = getenv("MVTV_FUSE_CFG");
@@ -859,7 +863,20 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   a.seq_red = ++red_seq;
   a.seq_halo = ++halo_seq;
   prof_begin(MVTV_KC_CG_INIT);
-  k_cg_init<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1});
+  if (P == 2 && init2d) {   // opt-in: marching / shuffle form (cg_init2d.cuh)
+    constexpr int IW = 4;
+    int occ = 1, nsm_i = 148;
+    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_init2d<T, IW>, 32 * IW, 0));
+    MVTV_CUDA(cudaDeviceGetAttribute(&nsm_i, cudaDevAttrMultiProcessorCount, device));
+    const long long tiles_i = ((long long)dt.m[0] + 64 * IW - 1) / (64 * IW);
+    long long nchunk = ((long long)nsm_i * std::max(occ, 1) + tiles_i - 1) / tiles_i;
+    nchunk = std::max(1ll, std::min<long long>(nchunk, std::max(1, dt.nz / 8)));
+    const int zchunk_i = (int)((dt.nz + nchunk - 1) / nchunk);
+    nchunk = (dt.nz + zchunk_i - 1) / zchunk_i;
+    k_cg_init2d<T, IW><<<dim3((unsigned)tiles_i, (unsigned)nchunk, 1), 32 * IW, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1}, zchunk_i);
+  } else {
+    k_cg_init<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1});
+  }
   prof_end();
   MVTV_CUDA(cudaGetLastError());
   launches += 1;

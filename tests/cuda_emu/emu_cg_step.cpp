@@ -18,6 +18,7 @@
 #include "../../multivartv_b200/csrc/cg_step2d.cuh"
 #include "../../multivartv_b200/csrc/cg_step3d.cuh"
 #include "../../multivartv_b200/csrc/cg_fused2d.cuh"
+#include "../../multivartv_b200/csrc/cg_init2d.cuh"
 // clang-format on
 
 using namespace mvtv;
@@ -474,6 +475,53 @@ static void check_fused(const char *name, std::vector<long long> m, const std::v
   }
 }
 
+
+// ---- k_cg_init2d (marching / shuffle form) against k_cg_init (gather form, GPU-validated) and the host loop
+static void check_init2d(std::vector<long long> m, const std::vector<double> &deltas, unsigned seed) {
+  Problem pb = make_problem(m, deltas, seed);
+  const DimTab dt = pb.M.dt;
+  const StencilTab st = pb.M.st;
+  std::mt19937_64 g(seed + 7);
+  std::normal_distribution<double> nd(0.0, 1.0);
+  std::vector<double> oty((size_t)dt.usz, 0.0), v1 = oty, v2 = oty;
+  for (long long i = dt.plane; i < dt.plane + dt.Nloc; ++i) { oty[(size_t)i] = nd(g); v1[(size_t)i] = nd(g); v2[(size_t)i] = nd(g); }
+  const double rho = 1.3, usc = 0.5;
+  auto run = [&](int which, int nchunk, std::vector<double> &r, std::vector<double> &xold, std::vector<double> &S) {
+    std::vector<double> x = pb.x, c = pb.c, dinv = pb.dinv;
+    r.assign((size_t)dt.usz, 0.0);
+    xold.assign((size_t)dt.usz, 0.0);
+    S.assign(CS_N, -1.0);
+    CgArgs<double> a{};
+    a.x = x.data(); a.xold = xold.data(); a.r = r.data(); a.c = c.data(); a.dinv = dinv.data(); a.oty = oty.data(); a.v1 = v1.data(); a.v2 = v2.data();
+    a.S = S.data(); a.rho = rho; a.uscale = usc; a.rhoM = pb.rhoM; a.rtol2 = 1e-26;
+    std::vector<double> partials((size_t)(1 << 16) * 3, 0.0);
+    unsigned counter = 0;
+    if (which == 0) {
+      cuda_emu::launch(dim3((unsigned)((dt.plane + 255) / 256), (unsigned)dt.nz, 1), dim3(256, 1, 1), 0,
+                       [&] { k_cg_init<double, 2>(dt, st, a, RedBuf{partials.data(), &counter}); });
+    } else {
+      const int zchunk = (dt.nz + nchunk - 1) / nchunk;
+      cuda_emu::launch(dim3((unsigned)((dt.m[0] + 255) / 256), (unsigned)((dt.nz + zchunk - 1) / zchunk), 1), dim3(128, 1, 1), 0,
+                       [&] { k_cg_init2d<double, 4>(dt, st, a, RedBuf{partials.data(), &counter}, zchunk); });
+    }
+  };
+  std::vector<double> r0, xo0, S0, r1, xo1, S1;
+  run(0, 1, r0, xo0, S0);
+  for (int nchunk = 1; nchunk <= 3; ++nchunk) {
+    run(1, nchunk, r1, xo1, S1);
+    double er = 0, ex = 0, es = 0;
+    for (long long i = dt.plane; i < dt.plane + dt.Nloc; ++i) {
+      er = std::max(er, std::fabs(r0[(size_t)i] - r1[(size_t)i]));
+      ex = std::max(ex, std::fabs(xo0[(size_t)i] - xo1[(size_t)i]));
+    }
+    for (int k : {CS_RZ0, CS_RR0, CS_BB, CS_ITERS, CS_PQ}) es = std::max(es, std::fabs(S0[(size_t)k] - S1[(size_t)k]) / std::max(1.0, std::fabs(S0[(size_t)k])));
+    if (!(er <= 1e-12 && ex == 0.0 && es <= 1e-12)) {
+      ++g_fail;
+      std::printf("FAIL init2d mesh=%lldx%lld chunks=%d: r %.2e xold %.2e scalars %.2e\n", dt.m[0], dt.m[1], nchunk, er, ex, es);
+    }
+  }
+}
+
 int main() {
   const std::vector<double> none, d2 = {0.5, 0.25}, d3 = {0.3, 0.5, 2.0};
   // 2-D: the GPU-validated pair first (this validates the emulator itself)
@@ -495,6 +543,10 @@ int main() {
       check_fused<Fused2dCfg<8, 0>>("<8>", m, none, 21 + (unsigned)iters, iters);
       check_fused<Fused2dCfg<4, 0>>("<4>", m, d2, 31 + (unsigned)iters, iters);
     }
+  for (auto m : std::vector<std::vector<long long>>{{66, 5}, {130, 9}, {2, 7}, {258, 4}, {64, 12}}) {
+    check_init2d(m, none, 41);
+    check_init2d(m, d2, 42);
+  }
   check_slabs_all<STEP_JACOBI>(11);
   check_slabs_all<STEP_Z>(12);
   check_slabs_all<STEP_PREC>(13);

@@ -14,7 +14,7 @@ from bench import synth_points  # noqa: E402
 
 
 def run(m, x, y, axes, env, passes):
-    for k in ("MVTV_FUSE_UPDPREC", "MVTV_FUSE_CFG"):
+    for k in ("MVTV_FUSE_UPDPREC", "MVTV_FUSE_CFG", "MVTV_INIT2D"):
         os.environ.pop(k, None)
     os.environ.update(env)
     with mv.Plan(m) as plan:
@@ -33,8 +33,9 @@ def main():
         x, y = synth_points(n, 2, 5)
         axes = [np.linspace(0.0, 1.0, d) for d in m]
         ref, _ = run(m, x, y, axes, {}, 12)
-        for cfg in range(4):
-            got, _ = run(m, x, y, axes, {"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": str(cfg)}, 12)
+        for cfg in range(5):
+            env = {"MVTV_INIT2D": "1"} if cfg == 4 else {"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": str(cfg)}   # 4: marching k_cg_init2d alone
+            got, _ = run(m, x, y, axes, env, 12)
             err = float(np.abs(got["theta"] - ref["theta"]).max())
             print("parity m=%s cfg=%d: max|dtheta|=%.2e passes %d vs %d inner %d vs %d %s" % (
                 m, cfg, err, got["passes"], ref["passes"], got["inner_iters"], ref["inner_iters"],
@@ -42,12 +43,13 @@ def main():
     m, n = [4096, 4096], 1 << 24
     x, y = synth_points(n, 2, 117)
     axes = [np.linspace(0.0, 1.0, d) for d in m]
-    for name, env in [("separate", {})] + [("fused%d" % c, {"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": str(c)}) for c in range(4)]:
+    for name, env in [("separate", {}), ("init2d", {"MVTV_INIT2D": "1"})] + [("fused%d" % c, {"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": str(c)}) for c in range(4)]:
         r, prof = run(m, x, y, axes, env, 10)
         inner = r["inner_iters"]
-        print("time %-9s ms/pass=%.3f inner/pass=%.1f  us/launch: step=%.1f update(+prec)=%.1f prec=%.1f" % (
+        print("time %-9s ms/pass=%.3f inner/pass=%.1f  us/launch: step=%.1f update(+prec)=%.1f prec=%.1f init=%.1f" % (
             name, 1e3 * r["device_seconds"] / r["passes"], inner / r["passes"], 1e3 * prof["cg_step"][0] / inner,
-            1e3 * prof["cg_update"][0] / inner, 1e3 * prof["cg_prec"][0] / max(1, prof["cg_prec"][1])), flush=True)
+            1e3 * prof["cg_update"][0] / inner, 1e3 * prof["cg_prec"][0] / max(1, prof["cg_prec"][1]),
+            1e3 * prof["cg_init"][0] / max(1, prof["cg_init"][1])), flush=True)
 
 
 if __name__ == "__main__":
