@@ -34,3 +34,14 @@ def test_cg_step_kernels_on_the_emulator(tmp_path):
     env = dict(os.environ, EMU_NEGATIVE="1")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 1 and "FAIL" in r.stdout
+
+
+def test_whole_admm_passes_on_the_emulator(tmp_path):
+    """tests/cuda_emu/emu_solve.cpp: the kernel pipeline of mvtv_solve driven on the emulator, GPU-validated kernels vs the opt-in
+    ones (k_cg_init2d, k_cg_updprec2d, k_cg_step3d, other z/u tiles): same theta and u after the passes, same CG iteration count.
+    The default run is the reduced set; MVTV_SLOW_TESTS=1 runs every combination (~6 min)."""
+    exe = _build(tmp_path, "emu_solve")
+    args = [exe] if os.environ.get("MVTV_SLOW_TESTS") == "1" else [exe, "quick"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "emu_solve: 0 failure(s)" in r.stdout and "FAIL" not in r.stdout
