@@ -16,6 +16,7 @@
 
 #include "cg_step2d.cuh"
 #include "cg_step3d.cuh"
+#include "cg_step3dh.cuh"
 #include "cg_fused2d.cuh"
 #include "cg_init2d.cuh"
 #include "kernels.cuh"
@@ -157,6 +158,7 @@ struct mvtv_plan {
   int fuse_cfg = 0;
   void *r2 = nullptr;          // second residual buffer of the fused kernel (allocated on first use)
   bool step3d = false;   // 3-D meshes: EXPERIMENTAL shuffle-based k_cg_step3d (MVTV_STEP3D=shfl), default off
+  bool step3dh = false;  // 3-D meshes: EXPERIMENTAL hybrid k_cg_step3dh (MVTV_STEP3D=hyb), default off
   int step3d_cfg = 0;
   bool step2d = false;   // 2-D meshes: shuffle-based k_cg_step2d (cg_step2d.cuh) instead of the shared-memory k_cg_step
   int zu_cfg = 0;        // tile variant of k_zu_march (MVTV_ZU_CFG), 0 = default
@@ -353,6 +355,7 @@ struct mvtv_plan {
       fuse_cfg = cf ? atoi(cf) : 0;
       const char *e3 = getenv("MVTV_STEP3D");
       step3d = e3 && std::string(e3) == "shfl" && P == 3 && (m[0] % 2 == 0) && m[0] >= 2;
+      step3dh = e3 && std::string(e3) == "hyb" && P == 3 && (m[0] % 2 == 0) && m[0] >= 2;
       const char *c4 = getenv("MVTV_STEP3D_CFG");
       step3d_cfg = c4 ? atoi(c4) : 0;
     }
@@ -1021,6 +1024,31 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     });
   }
   const int gu = (int)std::max<long long>(1, std::min<long long>(148 * 8, (dt.Nloc + 1023) / 1024));
+  // 3-D meshes, opt-in: the hybrid kernel (cg_step3dh.cuh); a warp owns one row of 64 vertices, a CTA TY rows + 2 halo rows
+  const bool use3dh = (P == 3) && step3dh;
+  auto dispatch3dh = [&](auto &&fn) {
+    switch (step3d_cfg) {
+      case 1: fn(Step3dhCfg<6, 2>{}); break;
+      case 2: fn(Step3dhCfg<14, 1>{}); break;
+      case 3: fn(Step3dhCfg<14, 2>{}); break;
+      case 4: fn(Step3dhCfg<10, 1>{}); break;
+      case 5: fn(Step3dhCfg<6, 1, false>{}); break;   // preconditioner reads diag(c)
+      case 6: fn(Step3dhCfg<2, 2>{}); break;          // 128 threads per CTA
+      default: fn(Step3dhCfg<6, 1>{}); break;
+    }
+  };
+  if (use3dh) {
+    dispatch3dh([&](auto cfg) {
+      using CH = decltype(cfg);
+      const unsigned tiles3 = (unsigned)(((m0 + CH::TX - 1) / CH::TX) * ((m1 + CH::TY - 1) / CH::TY));
+      int occ = 1, occp = 1;
+      if (prec) MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step3dh<T, CH, STEP_Z>, CH::NT, 0));
+      else MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step3dh<T, CH, STEP_JACOBI>, CH::NT, 0));
+      MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, k_cg_step3dh<T, CH, STEP_PREC>, CH::NT, 0));
+      gs = chunking2(tiles3, occ, zchunk);
+      gs_prec = chunking2(tiles3, occp, zchunk_prec);
+    });
+  }
   // 2-D, one GPU, polynomial preconditioner, opt-in: vector update fused with the preconditioner (cg_fused2d.cuh)
   const bool fused = use2d && prec && world == 1 && fuse_updprec;
   dim3 gs_fused = gs_prec;
@@ -1065,6 +1093,10 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
           using C3 = decltype(cfg);
           k_cg_step3d<T, C3, STEP_PREC><<<gs_prec, C3::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
         });
+        else if (use3dh) dispatch3dh([&](auto cfg) {
+          using CH = decltype(cfg);
+          k_cg_step3dh<T, CH, STEP_PREC><<<gs_prec, CH::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
+        });
         else k_cg_step<T, Cfg, STEP_PREC><<<gs_prec, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
         prof_end();
         if (d_peer) {
@@ -1089,6 +1121,12 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
           using C3 = decltype(cfg);
           if (prec) k_cg_step3d<T, C3, STEP_Z><<<gs, C3::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
           else k_cg_step3d<T, C3, STEP_JACOBI><<<gs, C3::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+        });
+      } else if (use3dh) {
+        dispatch3dh([&](auto cfg) {
+          using CH = decltype(cfg);
+          if (prec) k_cg_step3dh<T, CH, STEP_Z><<<gs, CH::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+          else k_cg_step3dh<T, CH, STEP_JACOBI><<<gs, CH::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
         });
       } else if (prec) k_cg_step<T, Cfg, STEP_Z><<<gs, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       else k_cg_step<T, Cfg, STEP_JACOBI><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
@@ -1522,13 +1560,14 @@ int mvtv_plan_describe(const mvtv_plan *plan, char *buf, int64_t cap) {
   return guarded([&] {
     MVTV_REQUIRE(plan && buf && cap > 0, "null argument");
     const bool s2 = plan->step2d && plan->dt.P == 2;
-    const bool s3 = plan->step3d && plan->dt.P == 3;
+    const bool s3 = (plan->step3d || plan->step3dh) && plan->dt.P == 3;
     char tmp[512];
     snprintf(tmp, sizeof(tmp),
              "{\"p\": %d, \"dtype\": %d, \"world\": %d, \"zu\": \"%s\", \"cg_step\": \"%s\", \"cg_prec\": \"%s\", "
              "\"cg_prec_words\": %d, \"collectives\": \"%s\"}",
              plan->p, plan->dtype, plan->world, plan->zu_variant >= 0 ? "k_zu_march" : "k_zu",
-             s2 ? "k_cg_step2d" : (s3 ? "k_cg_step3d" : "k_cg_step"), s2 ? "k_cg_step2d" : (s3 ? "k_cg_step3d" : "k_cg_step"),
+             s2 ? "k_cg_step2d" : (s3 ? (plan->step3dh ? "k_cg_step3dh" : "k_cg_step3d") : "k_cg_step"),
+             s2 ? "k_cg_step2d" : (s3 ? (plan->step3dh ? "k_cg_step3dh" : "k_cg_step3d") : "k_cg_step"),
              (s2 || (s3 && plan->step3d_cfg != 5)) ? 3 : 4,
              plan->world == 1 ? "none" : (plan->d_peer ? "peer" : "nccl"));
     MVTV_REQUIRE((int64_t)strlen(tmp) < cap, "buffer too small");

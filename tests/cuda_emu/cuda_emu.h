@@ -33,7 +33,7 @@
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {

@@ -17,6 +17,7 @@
 #include "../../multivartv_b200/csrc/zu_march.cuh"
 #include "../../multivartv_b200/csrc/cg_step2d.cuh"
 #include "../../multivartv_b200/csrc/cg_step3d.cuh"
+#include "../../multivartv_b200/csrc/cg_step3dh.cuh"
 #include "../../multivartv_b200/csrc/cg_fused2d.cuh"
 #include "../../multivartv_b200/csrc/cg_init2d.cuh"
 // clang-format on
@@ -137,7 +138,7 @@ struct Pipeline {
   const char *name;
   int zu = 0;       // tile variant of k_zu_march (as MVTV_ZU_CFG)
   bool init2d = false, fused = false;
-  int step = 0;     // 0: k_cg_step (shared memory), 1: k_cg_step2d / k_cg_step3d
+  int step = 0;     // 0: k_cg_step (shared memory), 1: k_cg_step2d / k_cg_step3d, 2: k_cg_step3dh
   int step_cfg = 0;
 };
 
@@ -235,6 +236,15 @@ static int cg_solve(const Tabs &T, const Pipeline &pl, State &s, double rho, dou
       const unsigned tiles = (unsigned)(((dt.m[0] + Old::TX - 1) / Old::TX) * ((dt.m[1] + Old::TY - 1) / Old::TY));
       if (mode == STEP_PREC) cuda_emu::launch(dim3(tiles, nch, 1), dim3(Old::NT, 1, 1), sizeof(double) * Old::smem_elems<STEP_PREC>(), [&] { k_cg_step<double, Old, STEP_PREC>(dt, st, a, rb, zchunk); });
       else cuda_emu::launch(dim3(tiles, nch, 1), dim3(Old::NT, 1, 1), sizeof(double) * Old::smem_elems<STEP_Z>(), [&] { k_cg_step<double, Old, STEP_Z>(dt, st, a, rb, zchunk); });
+    } else if (pl.step == 2) {
+      auto go = [&](auto cfg) {
+        using CH = decltype(cfg);
+        const unsigned tiles = (unsigned)(((dt.m[0] + CH::TX - 1) / CH::TX) * ((dt.m[1] + CH::TY - 1) / CH::TY));
+        if (mode == STEP_PREC) cuda_emu::launch(dim3(tiles, nch, 1), dim3(CH::NT, 1, 1), 0, [&] { k_cg_step3dh<double, CH, STEP_PREC>(dt, st, a, rb, zchunk); });
+        else cuda_emu::launch(dim3(tiles, nch, 1), dim3(CH::NT, 1, 1), 0, [&] { k_cg_step3dh<double, CH, STEP_Z>(dt, st, a, rb, zchunk); });
+      };
+      if (pl.step_cfg == 1) go(Step3dhCfg<6, 2>{});
+      else go(Step3dhCfg<6, 1>{});
     } else {
       auto go = [&](auto cfg) {
         using C3 = decltype(cfg);
@@ -339,7 +349,8 @@ int main(int argc, char **argv) {
   if (argc > 1 && std::string(argv[1]) == "quick") {   // the default CPU test: two passes, one mesh per dimension
     g_passes = 2;
     check({66, 6}, 1, {{"baseline (k_cg_step2d)", 0, false, false, 1, 0}, {"k_cg_step2d + init2d + fused", 0, true, true, 1, 0}});
-    check({12, 6, 4}, 3, {{"baseline (k_cg_step)", 0, false, false, 0, 0}, {"k_cg_step3d<4,2> + zu tile 1", 1, false, false, 1, 0}});
+    check({12, 6, 4}, 3, {{"baseline (k_cg_step)", 0, false, false, 0, 0}, {"k_cg_step3d<4,2> + zu tile 1", 1, false, false, 1, 0},
+                          {"k_cg_step3dh<6,2>", 0, false, false, 2, 1}});
     std::printf("emu_solve: %d failure(s)\n", g_fail);
     return g_fail ? 1 : 0;
   }
@@ -353,7 +364,9 @@ int main(int argc, char **argv) {
   const std::vector<Pipeline> p3 = {{"baseline (k_cg_step)", 0, false, false, 0, 0},
                                     {"k_cg_step3d<4,2>", 0, false, false, 1, 0},
                                     {"k_cg_step3d<4,4> + zu tile 1", 1, false, false, 1, 1},
-                                    {"k_cg_step3d<8,1> + zu tile 3", 3, false, false, 1, 6}};
+                                    {"k_cg_step3d<8,1> + zu tile 3", 3, false, false, 1, 6},
+                                    {"k_cg_step3dh<6,1>", 0, false, false, 2, 0},
+                                    {"k_cg_step3dh<6,2> + zu tile 1", 1, false, false, 2, 1}};
   check({12, 10, 6}, 3, p3);
   check({66, 5, 5}, 4, p3);
   std::printf("emu_solve: %d failure(s)\n", g_fail);

@@ -12,7 +12,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import multivartv_b200 as mv  # noqa: E402
 from bench import synth_points  # noqa: E402
 
-NCFG = 8
+NCFG = 8          # k_cg_step3d variants (MVTV_STEP3D=shfl)
+NCFG_HYB = 7      # k_cg_step3dh variants (MVTV_STEP3D=hyb)
 
 
 def run(m, x, y, axes, env, passes, precond, dtype=mv.F64):
@@ -39,19 +40,20 @@ def main():
         for precond in (mv.PRECOND_CHEB1, mv.PRECOND_JACOBI):
             ref, _, k0 = run(m, x, y, axes, {}, 12, precond)
             assert k0 == "k_cg_step"
-            for cfg in range(NCFG):
-                got, _, k1 = run(m, x, y, axes, {"MVTV_STEP3D": "shfl", "MVTV_STEP3D_CFG": str(cfg)}, 12, precond)
-                assert k1 == "k_cg_step3d"
+            for kind, cfg in [("shfl", c) for c in range(NCFG)] + [("hyb", c) for c in range(NCFG_HYB)]:
+                got, _, k1 = run(m, x, y, axes, {"MVTV_STEP3D": kind, "MVTV_STEP3D_CFG": str(cfg)}, 12, precond)
+                assert k1 == ("k_cg_step3d" if kind == "shfl" else "k_cg_step3dh")
                 err = float(np.abs(got["theta"] - ref["theta"]).max())
                 ok = err <= 1e-10 and got["passes"] == ref["passes"]
                 bad += not ok
-                print("parity m=%s precond=%d cfg=%d: max|dtheta|=%.2e inner %d vs %d %s" % (m, precond, cfg, err, got["inner_iters"], ref["inner_iters"], "ok" if ok else "MISMATCH"), flush=True)
+                print("parity m=%s precond=%d %s cfg=%d: max|dtheta|=%.2e inner %d vs %d %s" % (m, precond, kind, cfg, err, got["inner_iters"], ref["inner_iters"], "ok" if ok else "MISMATCH"), flush=True)
     print("parity mismatches:", bad, flush=True)
     sizes = [([256, 256, 256], 256 ** 3)] + ([([512, 512, 512], 1 << 26)] if "--big" in sys.argv else [])
     for m, n in sizes:
         x, y = synth_points(n, 3, 117)
         axes = [np.linspace(0.0, 1.0, d) for d in m]
-        for name, env in [("smem", {})] + [("shfl%d" % c, {"MVTV_STEP3D": "shfl", "MVTV_STEP3D_CFG": str(c)}) for c in range(NCFG)]:
+        for name, env in ([("smem", {})] + [("shfl%d" % c, {"MVTV_STEP3D": "shfl", "MVTV_STEP3D_CFG": str(c)}) for c in range(NCFG)]
+                          + [("hyb%d" % c, {"MVTV_STEP3D": "hyb", "MVTV_STEP3D_CFG": str(c)}) for c in range(NCFG_HYB)]):
             r, prof, _ = run(m, x, y, axes, env, 5, mv.PRECOND_CHEB1)
             inner = r["inner_iters"]
             print("time %s %-6s ms/pass=%.3f inner/pass=%.1f  us/launch: step=%.1f prec=%.1f update=%.1f" % (
