@@ -4,7 +4,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/round2_first_call.sh'
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 240 python tools/step3d_probe.py --big      > $OUT/r2_step3d_probe.log 2>&1; echo "step3d rc=$?"; grep -c " ok$" $OUT/r2_step3d_probe.log; grep "^time\|MISMATCH\|mismatches" $OUT/r2_step3d_probe.log | tail -24
+timeout 480 python tools/step3d_probe.py --big      > $OUT/r2_step3d_probe.log 2>&1; echo "step3d rc=$?"; grep -c " ok$" $OUT/r2_step3d_probe.log; grep "^time\|MISMATCH\|mismatches" $OUT/r2_step3d_probe.log | tail -40
 timeout 200 python tools/zu_probe.py --big          > $OUT/r2_zu_probe.log 2>&1;     echo "zu rc=$?";     tail -12 $OUT/r2_zu_probe.log
 timeout 120 python tools/fused_probe.py             > $OUT/r2_fused_probe.log 2>&1;  echo "fused rc=$?";  grep "^time\|MISMATCH" $OUT/r2_fused_probe.log
 timeout 60 python tools/step2d_probe_prec.py        > $OUT/r2_prec_probe.log 2>&1;   echo "prec rc=$?";   grep "^time\|MISMATCH" $OUT/r2_prec_probe.log
