@@ -545,17 +545,20 @@ def test_step2d_kernel_cross_check(mv, monkeypatch):
 @pytest.mark.skipif(__import__("os").environ.get("MVTV_EXPERIMENTAL") != "1",
                     reason="k_cg_step3d is opt-in (MVTV_STEP3D=shfl) and not yet validated on a GPU: set MVTV_EXPERIMENTAL=1")
 def test_step3d_kernel_cross_check_experimental(mv, monkeypatch):
-    """EXPERIMENTAL k_cg_step3d (cg_step3d.cuh) vs k_cg_step on 3-D meshes; see tools/step3d_probe.py."""
+    """EXPERIMENTAL k_cg_step3d (cg_step3d.cuh) and k_cg_step3dh (cg_step3dh.cuh) vs k_cg_step on 3-D meshes; see
+    tools/step3d_probe.py."""
+    names = {"shfl": "k_cg_step3d", "hyb": "k_cg_step3dh", "smem": "k_cg_step"}
     for dims, n in ([12, 12, 12], 2000), ([66, 5, 7], 1500), ([130, 33, 6], 9000):
         x, y = synth(90 + dims[0], n, 3, 0.0, 1.0, 0.5)
         axes = po.mesh_axes(x, dims, po.MODE_RCPP)
         res = {}
-        for which in ("shfl", "smem"):
+        for which in ("shfl", "hyb", "smem"):
             monkeypatch.setenv("MVTV_STEP3D", which)
             with mv.Plan(dims) as pl:
-                assert pl.describe()["cg_step"] == ("k_cg_step3d" if which == "shfl" else "k_cg_step")
+                assert pl.describe()["cg_step"] == names[which]
                 pl.set_points(x, y, axes)
                 res[which] = pl.solve(0.8, mode="rcpp", max_passes=30, precond=mv.PRECOND_CHEB1)
         monkeypatch.delenv("MVTV_STEP3D", raising=False)
-        assert res["shfl"]["passes"] == res["smem"]["passes"]
-        assert np.abs(res["shfl"]["theta"] - res["smem"]["theta"]).max() <= 1e-10
+        for which in ("shfl", "hyb"):
+            assert res[which]["passes"] == res["smem"]["passes"]
+            assert np.abs(res[which]["theta"] - res["smem"]["theta"]).max() <= 1e-10
