@@ -15,6 +15,7 @@
 #ifndef __CUDACC__
 #define __CUDACC__ 1
 #endif
+#include <setjmp.h>
 #include <ucontext.h>
 
 #include <algorithm>
@@ -50,8 +51,10 @@ inline const char *cudaGetErrorString(cudaError_t) { return "cuda_emu"; }
 namespace cuda_emu {
 
 struct Fiber {
-  ucontext_t ctx;
-  std::vector<char> stack;
+  ucontext_t ctx;          // only for the first entry; later switches are _setjmp / _longjmp (no signal-mask system call)
+  jmp_buf jb;
+  bool started = false;
+  char *stack = nullptr;   // from the pool below: allocated once, reused by every block (no re-zeroing)
   bool done = false;
   uint3 tid{0, 0, 0};
   int linear = 0;
@@ -65,6 +68,7 @@ struct State {
   uint3 bid{0, 0, 0};
   Fiber *cur = nullptr;
   ucontext_t sched;
+  jmp_buf sched_jb;
   std::vector<Fiber> fibers;
   int alive = 0;
   Barrier blockbar;
@@ -74,7 +78,9 @@ struct State {
   std::vector<unsigned char> smem;
   std::function<void()> body;
   unsigned long long progress = 0;
+  std::vector<char *> stack_pool;
 };
+static const size_t kStackBytes = 256 * 1024;
 inline State &g() {
   static State s;
   return s;
@@ -83,7 +89,7 @@ inline unsigned char *dyn_smem() { return g().smem.data(); }
 
 inline void yield() {
   State &s = g();
-  swapcontext(&s.cur->ctx, &s.sched);
+  if (_setjmp(s.cur->jb) == 0) _longjmp(s.sched_jb, 1);
 }
 // generic barrier over `count()` participants; count is re-evaluated while waiting because threads may exit meanwhile
 template <typename CountFn>
@@ -136,7 +142,7 @@ inline void fiber_entry() {
   s.alive -= 1;
   s.warp_alive[(size_t)(f->linear >> 5)] -= 1;
   s.progress += 1;
-  swapcontext(&f->ctx, &s.sched);
+  _longjmp(s.sched_jb, 1);
 }
 
 // launch<<<grid, block, smem>>>: `body` calls the kernel with its arguments
@@ -162,10 +168,11 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void(
           Fiber &f = s.fibers[(size_t)t];
           f.linear = t;
           f.tid = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
-          f.stack.resize(256 * 1024);
+          while (s.stack_pool.size() <= (size_t)t) s.stack_pool.push_back((char *)std::malloc(kStackBytes));
+          f.stack = s.stack_pool[(size_t)t];
           getcontext(&f.ctx);
-          f.ctx.uc_stack.ss_sp = f.stack.data();
-          f.ctx.uc_stack.ss_size = f.stack.size();
+          f.ctx.uc_stack.ss_sp = f.stack;
+          f.ctx.uc_stack.ss_size = kStackBytes;
           f.ctx.uc_link = &s.sched;
           makecontext(&f.ctx, (void (*)())fiber_entry, 0);
         }
@@ -176,7 +183,14 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void(
             Fiber &f = s.fibers[(size_t)t];
             if (f.done) continue;
             s.cur = &f;
-            swapcontext(&s.sched, &f.ctx);
+            if (_setjmp(s.sched_jb) == 0) {
+              if (!f.started) {
+                f.started = true;
+                setcontext(&f.ctx);
+              } else {
+                _longjmp(f.jb, 1);
+              }
+            }
           }
           idle_rounds = (s.progress == before) ? idle_rounds + 1 : 0;
           if (idle_rounds > 4) {

@@ -4,7 +4,7 @@
 // once with each opt-in combination (k_cg_init2d, k_cg_updprec2d with its out-of-place residual, k_cg_step3d, other z/u tiles).
 // theta and u after the passes must agree: this checks what the per-kernel drivers cannot -- the parity-selected buffers and
 // scalar slots across iterations, the first-iteration preconditioner call of the fused path, chunking choices interacting.
-//   usage: emu_solve [quick]     (exit code 0 = all combinations agree with the baseline pipeline; the full run takes ~6 min)
+//   usage: emu_solve [quick]     (exit code 0 = all combinations agree with the baseline pipeline; the full run takes ~30 s, `quick` a reduced set)
 #include <cstdio>
 #include <functional>
 #include <random>
