@@ -19,6 +19,7 @@
 #include "cg_step3dh.cuh"
 #include "cg_fused2d.cuh"
 #include "cg_init2d.cuh"
+#include "cg_horner2d.cuh"
 #include "kernels.cuh"
 #include "setup.h"
 #include "zu_march.cuh"
@@ -153,6 +154,9 @@ struct mvtv_plan {
   unsigned long long red_seq = 0, halo_seq = 0, zhalo_seq = 0;
   double cheb_bmax = 0.0;   // bound on the spectrum of D^-1 (diag(c) + s D^T D), independent of s and c
   int step2d_cfg = 0, step2d_prec_cfg = 0;   // tile variants of k_cg_step2d (MVTV_STEP2D_CFG, MVTV_STEP2D_PREC_CFG)
+  int cheb_degree = 1;         // 2-D, one GPU: EXPERIMENTAL degree 2..4 polynomial preconditioner (MVTV_CHEB_DEGREE), default 1
+  double cheb_kappa = 30.0;    // the polynomial is the Chebyshev one on [bmax/kappa, bmax] (MVTV_CHEB_KAPPA)
+  int horner_cfg = 0;          // MVTV_HORNER_CFG: 0 = 4 CTAs of 256 threads per SM (64 registers, 8..40 bytes spilled), 1 = 3 CTAs (85 registers)
   bool init2d = false;         // 2-D: EXPERIMENTAL marching k_cg_init2d (MVTV_INIT2D=1), default off
   bool fuse_updprec = false;   // 2-D, one GPU: EXPERIMENTAL k_cg_updprec2d (MVTV_FUSE_UPDPREC=1), default off
   int fuse_cfg = 0;
@@ -347,6 +351,13 @@ struct mvtv_plan {
       step2d_cfg = c2 ? atoi(c2) : 0;
       const char *c3 = getenv("MVTV_STEP2D_PREC_CFG");
       step2d_prec_cfg = c3 ? atoi(c3) : 0;
+      const char *ed = getenv("MVTV_CHEB_DEGREE");
+      cheb_degree = ed ? std::max(1, std::min(4, atoi(ed))) : 1;
+      if (!(step2d && world == 1)) cheb_degree = 1;
+      const char *ek = getenv("MVTV_CHEB_KAPPA");
+      cheb_kappa = ek ? std::max(2.0, atof(ek)) : 30.0;
+      const char *eh = getenv("MVTV_HORNER_CFG");
+      horner_cfg = eh ? atoi(eh) : 0;
       const char *ei = getenv("MVTV_INIT2D");
       init2d = ei && std::string(ei) == "1" && step2d;
       const char *ef = getenv("MVTV_FUSE_UPDPREC");
@@ -1050,7 +1061,18 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     });
   }
   // 2-D, one GPU, polynomial preconditioner, opt-in: vector update fused with the preconditioner (cg_fused2d.cuh)
-  const bool fused = use2d && prec && world == 1 && fuse_updprec;
+  const bool horner = use2d && prec && world == 1 && cheb_degree >= 2;   // opt-in: degree-d polynomial, one stencil pass per degree
+  double hc[8] = {0};
+  dim3 gs_horner = gs_prec;
+  int zchunk_horner = zchunk_prec;
+  if (horner) {
+    cheb_poly_coeffs(cheb_degree, cheb_bmax, cheb_kappa, hc);
+    int occ = 1;
+    if (horner_cfg == 1) MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_horner2d<T, 8, 3, false>, 256, 0));
+    else MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_horner2d<T, 8, 4, false>, 256, 0));
+    gs_horner = chunking2((unsigned)((m0 + 64 * 8 - 1) / (64 * 8)), occ, zchunk_horner);
+  }
+  const bool fused = use2d && prec && world == 1 && fuse_updprec && !horner;
   dim3 gs_fused = gs_prec;
   int zchunk_fused = zchunk_prec;
   auto dispatch_fused = [&](auto &&fn) {
@@ -1085,7 +1107,22 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
         a.seq_red = ++red_seq;
         a.seq_zhalo = ++zhalo_seq;
         prof_begin(MVTV_KC_CG_PREC);
-        if (use2d) dispatch2d_prec([&](auto cfg) {
+        if (horner) {
+          const int d = cheb_degree;
+          for (int j = 1; j <= d; ++j) {   // pass j writes z when d - j is even, the (free) q buffer otherwise
+            T *w_out = ((d - j) % 2 == 0) ? (T *)zbuf : (T *)q;
+            const T *w_in = ((d - j) % 2 == 0) ? (const T *)q : (const T *)zbuf;
+            const RedBuf rbh{partials, counters + 5};
+            if (horner_cfg == 1) {
+              if (j == 1) k_cg_horner2d<T, 8, 3, true><<<gs_horner, 256, 0, stream>>>(dt, st, a, nullptr, w_out, hc[d - 1], hc[d], j == d, rbh, zchunk_horner);
+              else k_cg_horner2d<T, 8, 3, false><<<gs_horner, 256, 0, stream>>>(dt, st, a, w_in, w_out, hc[d - j], 0.0, j == d, rbh, zchunk_horner);
+            } else {
+              if (j == 1) k_cg_horner2d<T, 8, 4, true><<<gs_horner, 256, 0, stream>>>(dt, st, a, nullptr, w_out, hc[d - 1], hc[d], j == d, rbh, zchunk_horner);
+              else k_cg_horner2d<T, 8, 4, false><<<gs_horner, 256, 0, stream>>>(dt, st, a, w_in, w_out, hc[d - j], 0.0, j == d, rbh, zchunk_horner);
+            }
+          }
+          launches += d - 1;
+        } else if (use2d) dispatch2d_prec([&](auto cfg) {
           using C2 = decltype(cfg);
           k_cg_step2d<T, C2, STEP_PREC><<<gs_prec, C2::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
         });

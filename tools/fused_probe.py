@@ -1,4 +1,4 @@
-"""Probe (round 2): the EXPERIMENTAL fused vector-update + preconditioner kernel k_cg_updprec2d (MVTV_FUSE_UPDPREC=1) against
+"""Probe (round 2): the EXPERIMENTAL degree 2..4 polynomial preconditioner k_cg_horner2d (MVTV_CHEB_DEGREE) and the EXPERIMENTAL fused vector-update + preconditioner kernel k_cg_updprec2d (MVTV_FUSE_UPDPREC=1) against
 the separate k_cg_update + k_cg_step2d<STEP_PREC> on 2-D meshes: parity on awkward shapes, then ms/pass on 4096^2.
 
     python tools/fused_probe.py
@@ -14,7 +14,7 @@ from bench import synth_points  # noqa: E402
 
 
 def run(m, x, y, axes, env, passes):
-    for k in ("MVTV_FUSE_UPDPREC", "MVTV_FUSE_CFG", "MVTV_INIT2D"):
+    for k in ("MVTV_FUSE_UPDPREC", "MVTV_FUSE_CFG", "MVTV_INIT2D", "MVTV_CHEB_DEGREE", "MVTV_CHEB_KAPPA", "MVTV_HORNER_CFG"):
         os.environ.pop(k, None)
     os.environ.update(env)
     with mv.Plan(m) as plan:
@@ -40,13 +40,21 @@ def main():
             print("parity m=%s cfg=%d: max|dtheta|=%.2e passes %d vs %d inner %d vs %d %s" % (
                 m, cfg, err, got["passes"], ref["passes"], got["inner_iters"], ref["inner_iters"],
                 "ok" if err <= 1e-10 and got["passes"] == ref["passes"] else "MISMATCH"), flush=True)
+        for deg in (2, 3, 4):   # k_cg_horner2d: another preconditioner, so the CG path differs; theta agrees to the CG tolerance
+            got, _ = run(m, x, y, axes, {"MVTV_CHEB_DEGREE": str(deg)}, 12)
+            err = float(np.abs(got["theta"] - ref["theta"]).max())
+            print("parity m=%s horner degree %d: max|dtheta|=%.2e passes %d vs %d inner %d vs %d %s" % (
+                m, deg, err, got["passes"], ref["passes"], got["inner_iters"], ref["inner_iters"],
+                "ok" if err <= 1e-9 and got["passes"] == ref["passes"] else "MISMATCH"), flush=True)
     m, n = [4096, 4096], 1 << 24
     x, y = synth_points(n, 2, 117)
     axes = [np.linspace(0.0, 1.0, d) for d in m]
-    for name, env in [("separate", {}), ("init2d", {"MVTV_INIT2D": "1"})] + [("fused%d" % c, {"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": str(c)}) for c in range(4)]:
+    for name, env in [("separate", {}), ("init2d", {"MVTV_INIT2D": "1"})] + [("fused%d" % c, {"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": str(c)}) for c in range(4)] + [
+            ("horner%d/k%d" % (d, k), {"MVTV_CHEB_DEGREE": str(d), "MVTV_CHEB_KAPPA": str(k)}) for d in (2, 3, 4) for k in (30, 100)] + [
+            ("horner3/k30/c1", {"MVTV_CHEB_DEGREE": "3", "MVTV_HORNER_CFG": "1"})]:
         r, prof = run(m, x, y, axes, env, 10)
         inner = r["inner_iters"]
-        print("time %-9s ms/pass=%.3f inner/pass=%.1f  us/launch: step=%.1f update(+prec)=%.1f prec=%.1f init=%.1f" % (
+        print("time %-14s ms/pass=%.3f inner/pass=%.1f  us/launch: step=%.1f update(+prec)=%.1f prec=%.1f init=%.1f" % (
             name, 1e3 * r["device_seconds"] / r["passes"], inner / r["passes"], 1e3 * prof["cg_step"][0] / inner,
             1e3 * prof["cg_update"][0] / inner, 1e3 * prof["cg_prec"][0] / max(1, prof["cg_prec"][1]),
             1e3 * prof["cg_init"][0] / max(1, prof["cg_init"][1])), flush=True)
