@@ -45,3 +45,31 @@ def test_whole_admm_passes_on_the_emulator(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=3000)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "emu_solve: 0 failure(s)" in r.stdout and "FAIL" not in r.stdout
+
+
+def test_whole_library_on_the_emulator(tmp_path):
+    """tests/cuda_emu/emu_lib_check.py: csrc/solver.cu + setup.cu themselves (launches rewritten by emu_translate.py, CUDA runtime
+    replaced by cuda_emu_rt.h) built into a scratch library and driven through the Python mirror in a subprocess: the default
+    path against the C oracle (Counter, theta, lambda path, operators) and the opt-in kernel paths against the default one, all
+    through the real host code (plan set-up, kernel selection, chunking, CG / ADMM drivers, C ABI).  MVTV_EMU_FULL=1 runs every
+    tile variant (~3 min) instead of the reduced set (~1.5 min, most of it the g++ build)."""
+    import sys
+    args = [sys.executable, os.path.join(EMU, "emu_lib_check.py"), str(tmp_path)]
+    if os.environ.get("MVTV_EMU_FULL") != "1":
+        args.append("quick")
+    r = subprocess.run(args, capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-3000:]
+    assert "emu_lib: 0 failure(s)" in r.stdout and "FAIL" not in r.stdout
+
+
+def test_launch_translation():
+    """emu_translate.py on the launch forms the library uses (template arguments, nested dim3, '->' in the configuration)."""
+    import sys
+    sys.path.insert(0, EMU)
+    from emu_translate import translate
+    src = ("if (a) k_x<T, Cfg<2, 3>, 1><<<dim3((unsigned)t, n, 1), Cfg::NT, smem, plan->stream>>>(dt, RedBuf{p, c + 5}, f(z));\n"
+           "else k_y<<<plan->grid(), 256>>>(a,\n   b);\n")
+    out, n = translate(src)
+    assert n == 2
+    assert "::cuda_emu::launch(dim3(dim3((unsigned)t, n, 1)), dim3(Cfg::NT), (size_t)(smem), [&] { k_x<T, Cfg<2, 3>, 1>(dt, RedBuf{p, c + 5}, f(z)); });" in out
+    assert "else ::cuda_emu::launch(dim3(plan->grid()), dim3(256), (size_t)(0), [&] { k_y(a,\n   b); });" in out
