@@ -156,6 +156,7 @@ struct mvtv_plan {
   int step2d_cfg = 0, step2d_prec_cfg = 0;   // tile variants of k_cg_step2d (MVTV_STEP2D_CFG, MVTV_STEP2D_PREC_CFG)
   int cheb_degree = 1;         // 2-D, one GPU: EXPERIMENTAL degree 2..4 polynomial preconditioner (MVTV_CHEB_DEGREE), default 1
   double cheb_kappa = 30.0;    // the polynomial is the Chebyshev one on [bmax/kappa, bmax] (MVTV_CHEB_KAPPA)
+  double cheb1_kappa = 30.0;   // interval of the degree-1 polynomial (MVTV_CHEB1_KAPPA; the measured default is 30)
   int horner_cfg = 0;          // MVTV_HORNER_CFG: 0 = 4 CTAs of 256 threads per SM (64 registers, 8..40 bytes spilled), 1 = 3 CTAs (85 registers)
   bool init2d = false;         // 2-D: EXPERIMENTAL marching k_cg_init2d (MVTV_INIT2D=1), default off
   bool fuse_updprec = false;   // 2-D, one GPU: EXPERIMENTAL k_cg_updprec2d (MVTV_FUSE_UPDPREC=1), default off
@@ -356,6 +357,8 @@ struct mvtv_plan {
       if (!(step2d && world == 1)) cheb_degree = 1;
       const char *ek = getenv("MVTV_CHEB_KAPPA");
       cheb_kappa = ek ? std::max(2.0, atof(ek)) : 30.0;
+      const char *e1 = getenv("MVTV_CHEB1_KAPPA");
+      cheb1_kappa = e1 ? std::max(2.0, atof(e1)) : 30.0;
       const char *eh = getenv("MVTV_HORNER_CFG");
       horner_cfg = eh ? atoi(eh) : 0;
       const char *ei = getenv("MVTV_INIT2D");
@@ -864,7 +867,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   a.prec = prec;
   {
     // degree-1 polynomial in D^-1 M whose residual 1 - t P(t) is the Chebyshev polynomial T2 on [bmax/30, bmax]
-    const double b = cheb_bmax, lo = b / 30.0, th = 0.5 * (b + lo), de = 0.5 * (b - lo);
+    const double b = cheb_bmax, lo = b / cheb1_kappa, th = 0.5 * (b + lo), de = 0.5 * (b - lo);
     const double T2 = 2.0 * (th / de) * (th / de) - 1.0;
     a.pc0 = 4.0 * th / (de * de * T2);
     a.pc1 = -2.0 / (de * de * T2);

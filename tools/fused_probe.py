@@ -29,30 +29,33 @@ def run(m, x, y, axes, env, passes):
 
 
 def main():
-    for m, n in (([100, 37], 3000), ([66, 5], 400), ([2, 9], 60), ([258, 33], 9000)):
+    tiny = "--tiny" in sys.argv
+    for m, n in (([66, 5], 400), ([2, 9], 60)) if tiny else (([100, 37], 3000), ([66, 5], 400), ([2, 9], 60), ([258, 33], 9000)):
         x, y = synth_points(n, 2, 5)
         axes = [np.linspace(0.0, 1.0, d) for d in m]
-        ref, _ = run(m, x, y, axes, {}, 12)
+        ref, _ = run(m, x, y, axes, {}, 2 if tiny else 12)
         for cfg in range(5):
             env = {"MVTV_INIT2D": "1"} if cfg == 4 else {"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": str(cfg)}   # 4: marching k_cg_init2d alone
-            got, _ = run(m, x, y, axes, env, 12)
+            got, _ = run(m, x, y, axes, env, 2 if tiny else 12)
             err = float(np.abs(got["theta"] - ref["theta"]).max())
             print("parity m=%s cfg=%d: max|dtheta|=%.2e passes %d vs %d inner %d vs %d %s" % (
                 m, cfg, err, got["passes"], ref["passes"], got["inner_iters"], ref["inner_iters"],
                 "ok" if err <= 1e-10 and got["passes"] == ref["passes"] else "MISMATCH"), flush=True)
         for deg in (2, 3, 4):   # k_cg_horner2d: another preconditioner, so the CG path differs; theta agrees to the CG tolerance
-            got, _ = run(m, x, y, axes, {"MVTV_CHEB_DEGREE": str(deg)}, 12)
+            got, _ = run(m, x, y, axes, {"MVTV_CHEB_DEGREE": str(deg)}, 2 if tiny else 12)
             err = float(np.abs(got["theta"] - ref["theta"]).max())
             print("parity m=%s horner degree %d: max|dtheta|=%.2e passes %d vs %d inner %d vs %d %s" % (
                 m, deg, err, got["passes"], ref["passes"], got["inner_iters"], ref["inner_iters"],
                 "ok" if err <= 1e-9 and got["passes"] == ref["passes"] else "MISMATCH"), flush=True)
     m, n = [4096, 4096], 1 << 24
+    if "--tiny" in sys.argv:   # dry run on the CPU emulator (tests/cuda_emu/emu_run.py): only the code path matters
+        m, n = [64, 48], 3000
     x, y = synth_points(n, 2, 117)
     axes = [np.linspace(0.0, 1.0, d) for d in m]
     for name, env in [("separate", {}), ("init2d", {"MVTV_INIT2D": "1"})] + [("fused%d" % c, {"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": str(c)}) for c in range(4)] + [
-            ("horner%d/k%d" % (d, k), {"MVTV_CHEB_DEGREE": str(d), "MVTV_CHEB_KAPPA": str(k)}) for d in (2, 3, 4) for k in (30, 100)] + [
+            ("horner%d/k%d" % (d, k), {"MVTV_CHEB_DEGREE": str(d), "MVTV_CHEB_KAPPA": str(k)}) for d in (2, 3, 4) for k in (20, 30)] + [
             ("horner3/k30/c1", {"MVTV_CHEB_DEGREE": "3", "MVTV_HORNER_CFG": "1"})]:
-        r, prof = run(m, x, y, axes, env, 10)
+        r, prof = run(m, x, y, axes, env, 2 if "--tiny" in sys.argv else 10)
         inner = r["inner_iters"]
         print("time %-14s ms/pass=%.3f inner/pass=%.1f  us/launch: step=%.1f update(+prec)=%.1f prec=%.1f init=%.1f" % (
             name, 1e3 * r["device_seconds"] / r["passes"], inner / r["passes"], 1e3 * prof["cg_step"][0] / inner,

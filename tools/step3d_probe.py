@@ -20,7 +20,8 @@ def run(m, x, y, axes, env, passes, precond, dtype=mv.F64):
     for k in ("MVTV_STEP3D", "MVTV_STEP3D_CFG"):
         os.environ.pop(k, None)
     os.environ.update(env)
-    with mv.Plan(m, dtype=dtype) as plan:
+    variant = mv.VARIANT_REFERENCE if len(set(m)) == 1 else mv.VARIANT_INTENDED   # the reference operator exists on cubic meshes only
+    with mv.Plan(m, dtype=dtype, variant=variant) as plan:
         kern = plan.describe()["cg_step"]
         plan.set_points(x, y, axes)
         kw = dict(mode="rcpp", cg_rtol=1e-13 if dtype == mv.F64 else 1e-5, want_fitted=False, raise_on_nonconvergence=False, precond=precond)
@@ -34,14 +35,15 @@ def run(m, x, y, axes, env, passes, precond, dtype=mv.F64):
 
 def main():
     bad = 0
-    for m, n in (([12, 12, 12], 2000), ([66, 5, 7], 1500), ([2, 9, 4], 60), ([130, 33, 6], 9000), ([20, 3, 20], 900)):
+    tiny = "--tiny" in sys.argv   # dry run on the CPU emulator (tests/cuda_emu/emu_run.py): two small meshes
+    for m, n in (([8, 8, 8], 600), ([66, 3, 4], 500)) if tiny else (([12, 12, 12], 2000), ([66, 5, 7], 1500), ([2, 9, 4], 60), ([130, 33, 6], 9000), ([20, 3, 20], 900)):
         x, y = synth_points(n, 3, 5)
         axes = [np.linspace(0.0, 1.0, d) for d in m]
         for precond in (mv.PRECOND_CHEB1, mv.PRECOND_JACOBI):
-            ref, _, k0 = run(m, x, y, axes, {}, 12, precond)
+            ref, _, k0 = run(m, x, y, axes, {}, 2 if tiny else 12, precond)
             assert k0 == "k_cg_step"
             for kind, cfg in [("shfl", c) for c in range(NCFG)] + [("hyb", c) for c in range(NCFG_HYB)]:
-                got, _, k1 = run(m, x, y, axes, {"MVTV_STEP3D": kind, "MVTV_STEP3D_CFG": str(cfg)}, 12, precond)
+                got, _, k1 = run(m, x, y, axes, {"MVTV_STEP3D": kind, "MVTV_STEP3D_CFG": str(cfg)}, 2 if tiny else 12, precond)
                 assert k1 == ("k_cg_step3d" if kind == "shfl" else "k_cg_step3dh")
                 err = float(np.abs(got["theta"] - ref["theta"]).max())
                 ok = err <= 1e-10 and got["passes"] == ref["passes"]
@@ -49,12 +51,14 @@ def main():
                 print("parity m=%s precond=%d %s cfg=%d: max|dtheta|=%.2e inner %d vs %d %s" % (m, precond, kind, cfg, err, got["inner_iters"], ref["inner_iters"], "ok" if ok else "MISMATCH"), flush=True)
     print("parity mismatches:", bad, flush=True)
     sizes = [([256, 256, 256], 256 ** 3)] + ([([512, 512, 512], 1 << 26)] if "--big" in sys.argv else [])
+    if "--tiny" in sys.argv:   # dry run on the CPU emulator (tests/cuda_emu/emu_run.py): only the code path matters
+        sizes = [([16, 16, 16], 4000)]
     for m, n in sizes:
         x, y = synth_points(n, 3, 117)
         axes = [np.linspace(0.0, 1.0, d) for d in m]
         for name, env in ([("smem", {})] + [("shfl%d" % c, {"MVTV_STEP3D": "shfl", "MVTV_STEP3D_CFG": str(c)}) for c in range(NCFG)]
                           + [("hyb%d" % c, {"MVTV_STEP3D": "hyb", "MVTV_STEP3D_CFG": str(c)}) for c in range(NCFG_HYB)]):
-            r, prof, _ = run(m, x, y, axes, env, 5, mv.PRECOND_CHEB1)
+            r, prof, _ = run(m, x, y, axes, env, 2 if "--tiny" in sys.argv else 5, mv.PRECOND_CHEB1)
             inner = r["inner_iters"]
             print("time %s %-6s ms/pass=%.3f inner/pass=%.1f  us/launch: step=%.1f prec=%.1f update=%.1f" % (
                 "x".join(map(str, m)), name, 1e3 * r["device_seconds"] / r["passes"], inner / r["passes"],

@@ -30,7 +30,8 @@ def run(m, x, y, axes, cfg, passes=4):
 def main():
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
     big = "--big" in sys.argv
-    for m in ([512] * 3 if big else [256] * 3, [96] * 4 if big else [48] * 4):
+    tiny = "--tiny" in sys.argv   # dry run on the CPU emulator (tests/cuda_emu/emu_run.py): only the code path matters
+    for m in ([16] * 3, [6] * 4) if tiny else ([512] * 3 if big else [256] * 3, [96] * 4 if big else [48] * 4):
         N = int(np.prod(m))
         x, y = synth_points(N // 2 if len(m) == 3 else N, len(m), 117)
         axes = [np.linspace(0.0, 1.0, d) for d in m]
