@@ -46,6 +46,9 @@ def build_emulated_library(scratch):
         assert p.wait() == 0
     lib = os.path.join(scratch, "libmvtv_emu.so")
     subprocess.check_call([gxx, "-shared", "-o", lib] + objs + ["-ldl"])
+    alias = os.path.join(scratch, "libmvtv_b200.so")   # scratch-only alias so that `-L <scratch> -lmvtv_b200` (tests/cpp) links to the emulation
+    if not os.path.lexists(alias):
+        os.symlink("libmvtv_emu.so", alias)
     return lib
 
 
