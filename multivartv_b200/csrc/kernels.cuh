@@ -225,11 +225,11 @@ struct PeerTab {
   int *error;                                 // set when a wait times out (a peer died): results become NaN
 };
 
-#ifdef MVTV_CUDA_EMU   // tests/cuda_emu: the kernel source compiled for the CPU emulator (one thread at a time: plain accesses)
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { *p = v; }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) { return *p; }
-__device__ __forceinline__ void st_relaxed_sys(double *p, double v) { *p = v; }
-__device__ __forceinline__ double ld_relaxed_sys(const double *p) { return *p; }
+#ifdef MVTV_CUDA_EMU   // tests/cuda_emu: the kernel source compiled for the CPU emulator (ranks are host threads: host atomics)
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_relaxed_sys(double *p, double v) { __atomic_store(p, &v, __ATOMIC_RELAXED); }
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) { double v; __atomic_load(p, &v, __ATOMIC_RELAXED); return v; }
 #else
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

@@ -48,8 +48,9 @@ struct NcclApi {
 
   void load() {
     if (handle) return;
-    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    const char *names[] = {getenv("MVTV_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};   // MVTV_NCCL_LIB: a specific NCCL build
     for (const char *nm : names) {
+      if (!nm || !*nm) continue;
       handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
       if (handle) break;
     }

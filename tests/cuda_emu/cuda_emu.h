@@ -16,6 +16,7 @@
 #define __CUDACC__ 1
 #endif
 #include <setjmp.h>
+#include <time.h>
 #include <ucontext.h>
 
 #include <algorithm>
@@ -33,7 +34,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __grid_constant__
-#define __shared__ static
+#define __shared__ static thread_local   // one emulated device per host thread (multi-rank emulation: one thread per rank)
 #define __align__(n) __attribute__((aligned(n)))
 
 struct uint3 { unsigned x, y, z; };
@@ -82,7 +83,7 @@ struct State {
 };
 static const size_t kStackBytes = 256 * 1024;
 inline State &g() {
-  static State s;
+  static thread_local State s;   // per host thread: several ranks can run their kernels concurrently
   return s;
 }
 inline unsigned char *dyn_smem() { return g().smem.data(); }
@@ -152,7 +153,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void(
   s.block = block;
   s.body = body;
   const int nt = (int)(block.x * block.y * block.z);
-  if (nt % 32 != 0 || nt > 1024) { std::fprintf(stderr, "cuda_emu: block size %d\n", nt); std::abort(); }
+  if (nt < 1 || nt > 1024) { std::fprintf(stderr, "cuda_emu: block size %d\n", nt); std::abort(); }
+  const int nwarps = (nt + 31) / 32;   // the last warp may be partial (e.g. the <<<1, 1>>> commit kernels)
   s.smem.assign(smem_bytes + 64, 0);
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
@@ -161,9 +163,10 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void(
         s.fibers.assign((size_t)nt, Fiber());
         s.alive = nt;
         s.blockbar = Barrier();
-        s.warpbar.assign((size_t)(nt / 32), Barrier());
-        s.warp_alive.assign((size_t)(nt / 32), 32);
-        s.warpbuf.assign((size_t)nt, 0);
+        s.warpbar.assign((size_t)nwarps, Barrier());
+        s.warp_alive.assign((size_t)nwarps, 32);
+        s.warp_alive[(size_t)nwarps - 1] = nt - 32 * (nwarps - 1);
+        s.warpbuf.assign((size_t)nwarps * 32, 0);
         for (int t = 0; t < nt; ++t) {
           Fiber &f = s.fibers[(size_t)t];
           f.linear = t;
@@ -213,7 +216,11 @@ inline void __syncthreads() { ::cuda_emu::sync_block(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { ::cuda_emu::sync_warp(); }
 inline void __threadfence() {}
 inline void __threadfence_system() {}
-inline long long clock64() { return 0; }
+inline long long clock64() {   // ~2 ticks per nanosecond, so that peer_spin's time-out (kernels.cuh) also ends a stuck emulated wait
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 2ll * ((long long)ts.tv_sec * 1000000000ll + ts.tv_nsec);
+}
 template <typename T> inline T __ldcg(const T *p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline unsigned atomicInc(unsigned *addr, unsigned val) {

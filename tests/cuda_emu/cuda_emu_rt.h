@@ -1,7 +1,7 @@
 // cuda_emu_rt.h -- TEST INFRASTRUCTURE ONLY: host-side stand-ins for the part of the CUDA runtime API that csrc/solver.cu and
 // csrc/setup.cu call, so that the library's host code (after tests/cuda_emu/emu_translate.py has rewritten its <<<>>> launches)
 // compiles with g++ against the SIMT emulator of cuda_emu.h.  "Device" memory is host memory, streams are synchronous,
-// events are wall-clock stamps, one device with EMU_NSM (default 4) multiprocessors.  Multi-GPU entry points (IPC) fail.
+// events are wall-clock stamps, one device with EMU_NSM (default 4) multiprocessors; IPC handles carry raw pointers (ranks = threads of one process, emu_nccl.cpp).
 #pragma once
 #include <chrono>
 
@@ -62,6 +62,7 @@ inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *occ, F, in
 }
 template <typename F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+// ranks of the multi-rank emulation are threads of one process: an IPC handle carries the raw pointer
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof(*p)); return *p ? cudaSuccess : cudaErrorNotSupported; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }

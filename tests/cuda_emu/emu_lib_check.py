@@ -30,6 +30,11 @@ def build_emulated_library(scratch):
     """g++ build of the translated sources; returns the path of libmvtv_emu.so."""
     from emu_translate import translate
     csrc = os.path.join(ROOT, "multivartv_b200", "csrc")
+    lib = os.path.join(scratch, "libmvtv_emu.so")
+    newest = max(os.path.getmtime(os.path.join(d, f)) for d in (csrc, HERE, os.path.join(HERE, "fake"), os.path.join(ROOT, "include"))
+                 for f in os.listdir(d) if os.path.isfile(os.path.join(d, f)))
+    if os.path.exists(lib) and os.path.getmtime(lib) >= newest and os.environ.get("EMU_REBUILD") != "1":
+        return lib   # a scratch directory shared by several checks is built once
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     objs, procs = [], []
     for name in ("solver", "setup"):
@@ -44,7 +49,6 @@ def build_emulated_library(scratch):
                                        "-I", os.path.join(HERE, "fake"), "-I", HERE, "-I", csrc, "-c", cpp, "-o", obj]))
     for p in procs:
         assert p.wait() == 0
-    lib = os.path.join(scratch, "libmvtv_emu.so")
     subprocess.check_call([gxx, "-shared", "-o", lib] + objs + ["-ldl"])
     alias = os.path.join(scratch, "libmvtv_b200.so")   # scratch-only alias so that `-L <scratch> -lmvtv_b200` (tests/cpp) links to the emulation
     if not os.path.lexists(alias):

@@ -19,11 +19,7 @@ def main():
     scratch = sys.argv[1]
     os.makedirs(scratch, exist_ok=True)
     import emu_lib_check
-    lib = os.path.join(scratch, "libmvtv_emu.so")
-    csrc = os.path.join(ROOT, "multivartv_b200", "csrc")
-    newest = max(os.path.getmtime(os.path.join(d, f)) for d in (csrc, HERE, os.path.join(ROOT, "include")) for f in os.listdir(d) if os.path.isfile(os.path.join(d, f)))
-    if not os.path.exists(lib) or os.path.getmtime(lib) < newest:
-        emu_lib_check.build_emulated_library(scratch)
+    lib = emu_lib_check.build_emulated_library(scratch)
     from multivartv_b200 import _lib, build
     _lib.LIB_PATH = lib                      # this process only
     _lib._lib = None

@@ -4,6 +4,9 @@ k_cg_step, k_cg_step2d and the not-yet-GPU-run k_cg_step3d with a host loop over
 by slab.  CPU test; says nothing about performance or PTX-level behaviour."""
 import os
 import subprocess
+import sys
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "cuda_emu")
@@ -47,14 +50,19 @@ def test_whole_admm_passes_on_the_emulator(tmp_path):
     assert "emu_solve: 0 failure(s)" in r.stdout and "FAIL" not in r.stdout
 
 
-def test_whole_library_on_the_emulator(tmp_path):
+@pytest.fixture(scope="module")
+def emu_scratch(tmp_path_factory):
+    """One scratch directory for the emulated library: built once (g++, ~1 min), shared by the checks below."""
+    return str(tmp_path_factory.mktemp("emu_lib"))
+
+
+def test_whole_library_on_the_emulator(emu_scratch):
     """tests/cuda_emu/emu_lib_check.py: csrc/solver.cu + setup.cu themselves (launches rewritten by emu_translate.py, CUDA runtime
     replaced by cuda_emu_rt.h) built into a scratch library and driven through the Python mirror in a subprocess: the default
     path against the C oracle (Counter, theta, lambda path, operators) and the opt-in kernel paths against the default one, all
     through the real host code (plan set-up, kernel selection, chunking, CG / ADMM drivers, C ABI).  MVTV_EMU_FULL=1 runs every
     tile variant (~3 min) instead of the reduced set (~1.5 min, most of it the g++ build)."""
-    import sys
-    args = [sys.executable, os.path.join(EMU, "emu_lib_check.py"), str(tmp_path)]
+    args = [sys.executable, os.path.join(EMU, "emu_lib_check.py"), emu_scratch]
     if os.environ.get("MVTV_EMU_FULL") != "1":
         args.append("quick")
     r = subprocess.run(args, capture_output=True, text=True, timeout=3000)
@@ -62,9 +70,18 @@ def test_whole_library_on_the_emulator(tmp_path):
     assert "emu_lib: 0 failure(s)" in r.stdout and "FAIL" not in r.stdout
 
 
+def test_multi_rank_path_on_the_emulator(emu_scratch):
+    """tests/cuda_emu/emu_multi_check.py: the slab-partitioned multi-GPU solve with every rank a host thread of one process --
+    peer-memory ghost planes / flags / rank-ordered reductions running concurrently, and the NCCL fallback over an in-process
+    NCCL stand-in (emu_nccl.cpp) -- world 2 and 3, 2-D / 3-D / 4-D, both preconditioners, against the single-process C oracle:
+    identical Counter, max|dtheta| <= 1e-9."""
+    r = subprocess.run([sys.executable, os.path.join(EMU, "emu_multi_check.py"), emu_scratch], capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-3000:]
+    assert "emu_multi: 0 failure(s)" in r.stdout and "FAIL" not in r.stdout
+
+
 def test_launch_translation():
     """emu_translate.py on the launch forms the library uses (template arguments, nested dim3, '->' in the configuration)."""
-    import sys
     sys.path.insert(0, EMU)
     from emu_translate import translate
     src = ("if (a) k_x<T, Cfg<2, 3>, 1><<<dim3((unsigned)t, n, 1), Cfg::NT, smem, plan->stream>>>(dt, RedBuf{p, c + 5}, f(z));\n"
