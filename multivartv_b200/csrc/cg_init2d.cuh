@@ -113,12 +113,18 @@ k_cg_init2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   double *S = a.S, *raw = a.raw;
   const PeerTab *peer = a.peer;
   const unsigned long long sr = a.seq_red, sh = a.seq_halo;
-  grid_reduce<3, 3>(red, rb, [S, raw, peer, sr, sh](const double (&res)[3]) {
+  const int fold = a.fold;
+  grid_reduce<3, 3>(red, rb, [S, raw, peer, sr, sh, fold](const double (&res)[3]) {
     if (peer) {
       __threadfence_system();
       if (peer->has_lo) st_release_sys(peer->hflag_at_prev, sh);
       if (peer->has_hi) st_release_sys(peer->hflag_at_next, sh);
       peer_post(*peer, sr, res, 3);
+      if (fold) {   // what k_cg_peer_commit_init does
+        double v[3];
+        peer_wait_sum(*peer, sr, v, 3);
+        cg_commit_init(S, v);
+      }
     } else if (raw) { raw[0] = res[0]; raw[1] = res[1]; raw[2] = res[2]; }
     else cg_commit_init(S, res);
   });

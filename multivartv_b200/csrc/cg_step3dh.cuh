@@ -202,7 +202,8 @@ k_cg_step3dh(const __grid_constant__ DimTab dt, const __grid_constant__ StencilT
   double *S = a.S, *raw = a.raw;
   const PeerTab *peer = a.peer;
   const unsigned long long sr = a.seq_red, sz = a.seq_zhalo;
-  grid_reduce<1, 1>(red, rb, [S, raw, peer, sr, sz](const double (&res)[1]) {
+  const int fold = a.fold;
+  grid_reduce<1, 1>(red, rb, [S, raw, peer, sr, sz, fold](const double (&res)[1]) {
     if (peer) {
       if (MODE == STEP_PREC) {
         __threadfence_system();
@@ -210,6 +211,12 @@ k_cg_step3dh(const __grid_constant__ DimTab dt, const __grid_constant__ StencilT
         if (peer->has_hi) st_release_sys(peer->zflag_at_next, sz);
       }
       peer_post(*peer, sr, res, 1);
+      if (fold) {   // what k_cg_peer_commit_rz / k_cg_peer_commit_pq do
+        double v[1];
+        peer_wait_sum(*peer, sr, v, 1);
+        if (MODE == STEP_PREC) cg_commit_rz(S, v);
+        else S[CS_PQ] = v[0];
+      }
     } else if (raw) raw[0] = res[0];
     else if (MODE == STEP_PREC) cg_commit_rz(S, res);
     else S[CS_PQ] = res[0];

@@ -303,6 +303,8 @@ struct CgArgs {
   T *z;            // polynomial preconditioner: z = P(D^-1 M) D^-1 r (ghosted slab)
   double pc0, pc1; // z = pc0*z0 + pc1*D^-1 M z0,  z0 = D^-1 r
   int prec;        // 0: Jacobi (z = D^-1 r formed on the fly), 1: degree-1 Chebyshev polynomial in D^-1 M
+  int fold;        // peer path, EXPERIMENTAL (MVTV_FOLD_COMMIT=1): the reducing kernel's last thread also waits for the world's
+                   // partials and commits the scalars, instead of a separate one-thread k_cg_peer_commit_* launch
 };
 
 __device__ __forceinline__ bool cg_done(const double *S, double rtol2) {
@@ -383,12 +385,18 @@ k_cg_init(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   double *S = a.S, *raw = a.raw;
   const PeerTab *peer = a.peer;
   const unsigned long long sr = a.seq_red, sh = a.seq_halo;
-  grid_reduce<3, 3>(red, rb, [S, raw, peer, sr, sh](const double (&res)[3]) {
+  const int fold = a.fold;
+  grid_reduce<3, 3>(red, rb, [S, raw, peer, sr, sh, fold](const double (&res)[3]) {
     if (peer) {
       __threadfence_system();
       if (peer->has_lo) st_release_sys(peer->hflag_at_prev, sh);
       if (peer->has_hi) st_release_sys(peer->hflag_at_next, sh);
       peer_post(*peer, sr, res, 3);
+      if (fold) {   // what k_cg_peer_commit_init does
+        double v[3];
+        peer_wait_sum(*peer, sr, v, 3);
+        cg_commit_init(S, v);
+      }
     } else if (raw) { raw[0] = res[0]; raw[1] = res[1]; raw[2] = res[2]; }
     else cg_commit_init(S, res);
   });
@@ -719,7 +727,8 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   double *S = a.S, *raw = a.raw;
   const PeerTab *peer = a.peer;
   const unsigned long long sr = a.seq_red, sz = a.seq_zhalo;
-  grid_reduce<1, 1>(red, rb, [S, raw, peer, sr, sz](const double (&res)[1]) {
+  const int fold = a.fold;
+  grid_reduce<1, 1>(red, rb, [S, raw, peer, sr, sz, fold](const double (&res)[1]) {
     if (peer) {
       if (MODE == STEP_PREC) {
         __threadfence_system();
@@ -727,6 +736,12 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
         if (peer->has_hi) st_release_sys(peer->zflag_at_next, sz);
       }
       peer_post(*peer, sr, res, 1);
+      if (fold) {   // what k_cg_peer_commit_rz / k_cg_peer_commit_pq do
+        double v[1];
+        peer_wait_sum(*peer, sr, v, 1);
+        if (MODE == STEP_PREC) cg_commit_rz(S, v);
+        else S[CS_PQ] = v[0];
+      }
     } else if (raw) raw[0] = res[0];
     else if (MODE == STEP_PREC) cg_commit_rz(S, res);
     else S[CS_PQ] = res[0];
@@ -784,12 +799,19 @@ k_cg_update(const CgArgs<T> a, const long long plane, const long long nloc, cons
   const PeerTab *peer = a.peer;
   const unsigned long long sr = a.seq_red, sh = a.seq_halo;
   const int prec = a.prec;
-  grid_reduce<2, 2>(red, rb, [S, raw, peer, sr, sh, prec](const double (&res)[2]) {
+  const int fold = a.fold;
+  grid_reduce<2, 2>(red, rb, [S, raw, peer, sr, sh, prec, fold](const double (&res)[2]) {
     if (peer) {
       __threadfence_system();
       if (peer->has_lo) st_release_sys(peer->hflag_at_prev, sh);
       if (peer->has_hi) st_release_sys(peer->hflag_at_next, sh);
       peer_post(*peer, sr, res, 2);
+      if (fold) {   // what k_cg_peer_commit_update / k_cg_peer_commit_update_prec do
+        double v[2];
+        peer_wait_sum(*peer, sr, v, 2);
+        if (prec) cg_commit_update_prec(S, v + 1);
+        else cg_commit_update(S, v);
+      }
     } else if (raw) { raw[0] = res[0]; raw[1] = res[1]; }
     else if (prec) cg_commit_update_prec(S, res + 1);
     else cg_commit_update(S, res);

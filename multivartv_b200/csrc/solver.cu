@@ -151,6 +151,7 @@ struct mvtv_plan {
   // peer-memory collectives of the CG loop (CUDA IPC); falls back to NCCL when unavailable or MVTV_COMM=nccl
   unsigned char *cb = nullptr;          // this rank's comm buffer (slots, flags, halo flags, error word)
   PeerTab *d_peer = nullptr;            // device copy of the peer table, nullptr = NCCL path
+  bool fold_commit = false;             // peer path, EXPERIMENTAL (MVTV_FOLD_COMMIT=1): no separate commit launches
   std::vector<void *> ipc_opened;
   unsigned long long red_seq = 0, halo_seq = 0, zhalo_seq = 0;
   double cheb_bmax = 0.0;   // bound on the spectrum of D^-1 (diag(c) + s D^T D), independent of s and c
@@ -358,6 +359,8 @@ struct mvtv_plan {
       if (!(step2d && world == 1)) cheb_degree = 1;
       const char *ek = getenv("MVTV_CHEB_KAPPA");
       cheb_kappa = ek ? std::max(2.0, atof(ek)) : 30.0;
+      const char *efc = getenv("MVTV_FOLD_COMMIT");
+      fold_commit = efc && std::string(efc) == "1";
       const char *e1 = getenv("MVTV_CHEB1_KAPPA");
       cheb1_kappa = e1 ? std::max(2.0, atof(e1)) : 30.0;
       const char *eh = getenv("MVTV_HORNER_CFG");
@@ -861,6 +864,8 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   a.S = S;
   a.raw = (world > 1 && !d_peer) ? raw : nullptr;
   a.peer = d_peer;
+  const bool fold = d_peer && fold_commit;   // opt-in: commits folded into the reducing kernels (no k_cg_peer_commit_* launches)
+  a.fold = fold ? 1 : 0;
   a.seq_red = 0;
   a.seq_halo = 0;
   a.seq_zhalo = 0;
@@ -898,7 +903,8 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   prof_end();
   MVTV_CUDA(cudaGetLastError());
   launches += 1;
-  if (d_peer) {
+  if (fold) {
+  } else if (d_peer) {
     k_cg_peer_commit_init<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red);
     launches += 1;
   } else if (world > 1) {
@@ -1140,14 +1146,15 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
         });
         else k_cg_step<T, Cfg, STEP_PREC><<<gs_prec, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
         prof_end();
-        if (d_peer) {
+        if (fold) {
+        } else if (d_peer) {
           k_cg_peer_commit_rz<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
         } else if (world > 1) {
           allreduce(raw, 1, ncclSum);
           k_cg_commit_rz<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
           exchange_ghosts<T>((T *)zbuf);
         }
-        launches += world > 1 ? 2 : 1;
+        launches += (world > 1 && !fold) ? 2 : 1;
       }
       a.seq_red = ++red_seq;       // a.seq_halo: the version the last producer of r posted
       prof_begin(MVTV_KC_CG_STEP);
@@ -1172,7 +1179,8 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       } else if (prec) k_cg_step<T, Cfg, STEP_Z><<<gs, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       else k_cg_step<T, Cfg, STEP_JACOBI><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
       prof_end();
-      if (d_peer) {
+      if (fold) {
+      } else if (d_peer) {
         k_cg_peer_commit_pq<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
       } else if (world > 1) {
         allreduce(raw, 1, ncclSum);
@@ -1187,7 +1195,8 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       });
       else k_cg_update<T><<<gu, 256, 0, stream>>>(a, dt.plane, dt.Nloc, RedBuf{partials, counters + 3});
       prof_end();
-      if (d_peer) {
+      if (fold) {
+      } else if (d_peer) {
         if (prec) k_cg_peer_commit_update_prec<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
         else k_cg_peer_commit_update<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
       } else if (world > 1) {
@@ -1195,7 +1204,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
         if (prec) k_cg_commit_update_prec<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
         else k_cg_commit_update<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
       }
-      launches += world > 1 ? 4 : 2;
+      launches += (world > 1 && !fold) ? 4 : 2;
     }
     MVTV_CUDA(cudaGetLastError());
     launched += batch;
@@ -1605,12 +1614,12 @@ int mvtv_plan_describe(const mvtv_plan *plan, char *buf, int64_t cap) {
     char tmp[512];
     snprintf(tmp, sizeof(tmp),
              "{\"p\": %d, \"dtype\": %d, \"world\": %d, \"zu\": \"%s\", \"cg_step\": \"%s\", \"cg_prec\": \"%s\", "
-             "\"cg_prec_words\": %d, \"collectives\": \"%s\"}",
+             "\"cg_prec_words\": %d, \"collectives\": \"%s\", \"fold_commit\": %d}",
              plan->p, plan->dtype, plan->world, plan->zu_variant >= 0 ? "k_zu_march" : "k_zu",
              s2 ? "k_cg_step2d" : (s3 ? (plan->step3dh ? "k_cg_step3dh" : "k_cg_step3d") : "k_cg_step"),
              s2 ? "k_cg_step2d" : (s3 ? (plan->step3dh ? "k_cg_step3dh" : "k_cg_step3d") : "k_cg_step"),
              (s2 || (s3 && plan->step3d_cfg != 5)) ? 3 : 4,
-             plan->world == 1 ? "none" : (plan->d_peer ? "peer" : "nccl"));
+             plan->world == 1 ? "none" : (plan->d_peer ? "peer" : "nccl"), (plan->d_peer && plan->fold_commit) ? 1 : 0);
     MVTV_REQUIRE((int64_t)strlen(tmp) < cap, "buffer too small");
     strcpy(buf, tmp);
     return MVTV_OK;

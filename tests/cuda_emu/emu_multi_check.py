@@ -42,15 +42,18 @@ def main():
     _lib.load()
 
     J, C1 = mv.PRECOND_JACOBI, mv.PRECOND_CHEB1
-    cases = [  # dims, n, mode, lambda, max_passes, preconditioner, world, comm
+    cases = [  # dims, n, mode, lambda, max_passes, preconditioner, world, comm ("fold": peer path with MVTV_FOLD_COMMIT=1)
         ([24, 22], 3000, "rcpp", 1.0, 8, C1, 2, "peer"), ([24, 22], 3000, "cpp", 3.0, 0, J, 2, "peer"),
         ([24, 23], 3000, "rcpp", 1.0, 6, C1, 3, "peer"), ([24, 22], 3000, "rcpp", 1.0, 6, C1, 2, "nccl"),
         ([8, 8, 9], 2000, "rcpp", 0.7, 5, C1, 2, "peer"), ([8, 8, 9], 2000, "rcpp", 0.7, 5, J, 3, "peer"),
         ([5, 5, 5, 7], 1500, "rcpp", 1.0, 4, C1, 2, "peer"), ([8, 8, 9], 2000, "cpp", 2.0, 0, C1, 2, "nccl"),
         ([23, 22], 3000, "rcpp", 1.0, 6, C1, 2, "peer"),   # odd width: the shared-memory k_cg_step instead of k_cg_step2d
+        ([24, 22], 3000, "rcpp", 1.0, 8, C1, 2, "fold"), ([24, 23], 3000, "cpp", 3.0, 0, J, 3, "fold"),
+        ([8, 8, 9], 2000, "rcpp", 0.7, 5, C1, 3, "fold"), ([5, 5, 5, 7], 1500, "rcpp", 1.0, 4, J, 2, "fold"),
+        ([23, 22], 3000, "rcpp", 1.0, 6, C1, 2, "fold"),
     ]
     if quick:
-        cases = [cases[0], cases[3], cases[4]]
+        cases = [cases[0], cases[3], cases[4], cases[9]]
     fail = 0
     for dims, n, mode, lam, max_passes, precond, world, comm in cases:
         p = len(dims)
@@ -59,10 +62,12 @@ def main():
         axes = mv.mesh_axes(x, dims, mode)
         variant = mv.VARIANT_REFERENCE if (p < 3 or len(set(dims)) == 1) else mv.VARIANT_INTENDED
         buckets = partition.bucket_points(x, y, axes[-1], world)
+        os.environ.pop("MVTV_COMM", None)
+        os.environ.pop("MVTV_FOLD_COMMIT", None)
         if comm == "nccl":
             os.environ["MVTV_COMM"] = "nccl"
-        else:
-            os.environ.pop("MVTV_COMM", None)
+        elif comm == "fold":
+            os.environ["MVTV_FOLD_COMMIT"] = "1"
         uid = mv.nccl_unique_id()
         results, errors = [None] * world, []
 
@@ -73,7 +78,7 @@ def main():
                     pl.set_points(buckets[rank][0], buckets[rank][1], axes)
                     out = pl.solve(lam, mode=mode, max_passes=max_passes, want_fitted=False, cg_rtol=1e-13, precond=precond,
                                    raise_on_nonconvergence=False)
-                    results[rank] = (pl.z0, out["theta"], out["counter"], out["inner_iters"], d)
+                    results[rank] = (pl.z0, out["theta"], out["counter"], out["inner_iters"], d, out["kernel_launches"])
             except Exception as e:   # noqa: BLE001
                 errors.append((rank, repr(e)))
 
@@ -91,11 +96,13 @@ def main():
         ref = co.mbs_one(x, y, dims, axes, lam, mode=imode, max_passes=max_passes, variant=variant)
         err = float(np.abs(theta - ref["theta"]).max())
         d = results[0][4]
-        good = all(r[2] == ref["counter"] for r in results) and err <= 1e-9 and d["collectives"] == comm and d["world"] == world
+        good = (all(r[2] == ref["counter"] for r in results) and err <= 1e-9 and d["world"] == world
+                and d["collectives"] == ("peer" if comm == "fold" else comm) and d["fold_commit"] == (1 if comm == "fold" else 0))
         fail += not good
-        print("%s dims=%s world=%d mode=%s precond=%d collectives=%s kernel=%s: Counter %d (oracle %d), %d CG iterations, max|dtheta| %.2e" % (
-            "ok  " if good else "FAIL", dims, world, mode, precond, d["collectives"], d["cg_step"], results[0][2], ref["counter"], results[0][3], err), flush=True)
+        print("%s dims=%s world=%d mode=%s precond=%d collectives=%s kernel=%s: Counter %d (oracle %d), %d CG iterations, %d launches, max|dtheta| %.2e" % (
+            "ok  " if good else "FAIL", dims, world, mode, precond, comm, d["cg_step"], results[0][2], ref["counter"], results[0][3], results[0][5], err), flush=True)
     os.environ.pop("MVTV_COMM", None)
+    os.environ.pop("MVTV_FOLD_COMMIT", None)
     print("emu_multi: %d failure(s)" % fail)
     return 1 if fail else 0
 
