@@ -52,6 +52,10 @@ def main():
         ([8, 8, 9], 2000, "rcpp", 0.7, 5, C1, 3, "fold"), ([5, 5, 5, 7], 1500, "rcpp", 1.0, 4, J, 2, "fold"),
         ([23, 22], 3000, "rcpp", 1.0, 6, C1, 2, "fold"),
     ]
+    for comm in ("peer", "fold", "nccl"):   # edge cases: one plane per rank, ranks without points, width 1 and 2, world 4
+        cases += [([6, 4], 200, "rcpp", 1.0, 4, C1, 4, comm), ([10, 5], 300, "cpp", 2.0, 0, J, 4, comm), ([4, 4, 4], 300, "rcpp", 0.7, 3, C1, 4, comm),
+                  ([3, 3, 3, 3], 300, "rcpp", 1.0, 3, J, 3, comm), ([7, 5], 100, "py", 0.8, 4, C1, 2, comm), ([2, 8], 50, "rcpp", 0.3, 4, C1, 4, comm),
+                  ([1, 6], 40, "cpp", 1.5, 0, C1, 3, comm), ([16, 7], 5, "rcpp", 1.0, 3, C1, 3, comm)]
     if quick:
         cases = [cases[0], cases[3], cases[4], cases[9]]
     fail = 0
