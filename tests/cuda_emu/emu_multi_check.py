@@ -56,10 +56,15 @@ def main():
         cases += [([6, 4], 200, "rcpp", 1.0, 4, C1, 4, comm), ([10, 5], 300, "cpp", 2.0, 0, J, 4, comm), ([4, 4, 4], 300, "rcpp", 0.7, 3, C1, 4, comm),
                   ([3, 3, 3, 3], 300, "rcpp", 1.0, 3, J, 3, comm), ([7, 5], 100, "py", 0.8, 4, C1, 2, comm), ([2, 8], 50, "rcpp", 0.3, 4, C1, 4, comm),
                   ([1, 6], 40, "cpp", 1.5, 0, C1, 3, comm), ([16, 7], 5, "rcpp", 1.0, 3, C1, 3, comm)]
+    for comm in ("peer", "fold"):          # the opt-in kernels that have a multi-GPU path (9th field: extra environment)
+        cases += [([12, 12, 12], 1500, "rcpp", 0.7, 3, C1, 2, comm, {"MVTV_STEP3D": "shfl"}), ([66, 4, 9], 2000, "rcpp", 1.0, 2, C1, 2, comm, {"MVTV_STEP3D": "hyb"}),
+                  ([8, 8, 8], 600, "rcpp", 0.7, 3, J, 3, comm, {"MVTV_STEP3D": "hyb", "MVTV_STEP3D_CFG": "1"}), ([24, 23], 3000, "rcpp", 1.0, 4, C1, 3, comm, {"MVTV_INIT2D": "1"})]
     if quick:
         cases = [cases[0], cases[3], cases[4], cases[9]]
     fail = 0
-    for dims, n, mode, lam, max_passes, precond, world, comm in cases:
+    for case in cases:
+        dims, n, mode, lam, max_passes, precond, world, comm = case[:8]
+        extra = case[8] if len(case) > 8 else {}
         p = len(dims)
         imode = {"cpp": 0, "rcpp": 1, "py": 2}[mode]
         x, y = synth(41 + p, n, p, 0.0, 1.0, 0.5)
@@ -72,6 +77,9 @@ def main():
             os.environ["MVTV_COMM"] = "nccl"
         elif comm == "fold":
             os.environ["MVTV_FOLD_COMMIT"] = "1"
+        for k in ("MVTV_STEP3D", "MVTV_STEP3D_CFG", "MVTV_INIT2D"):
+            os.environ.pop(k, None)
+        os.environ.update(extra)
         uid = mv.nccl_unique_id()
         results, errors = [None] * world, []
 
@@ -103,10 +111,12 @@ def main():
         good = (all(r[2] == ref["counter"] for r in results) and err <= 1e-9 and d["world"] == world
                 and d["collectives"] == ("peer" if comm == "fold" else comm) and d["fold_commit"] == (1 if comm == "fold" else 0))
         fail += not good
-        print("%s dims=%s world=%d mode=%s precond=%d collectives=%s kernel=%s: Counter %d (oracle %d), %d CG iterations, %d launches, max|dtheta| %.2e" % (
-            "ok  " if good else "FAIL", dims, world, mode, precond, comm, d["cg_step"], results[0][2], ref["counter"], results[0][3], results[0][5], err), flush=True)
+        print("%s dims=%s world=%d mode=%s precond=%d collectives=%s%s kernel=%s: Counter %d (oracle %d), %d CG iterations, %d launches, max|dtheta| %.2e" % (
+            "ok  " if good else "FAIL", dims, world, mode, precond, comm, (" " + str(extra)) if extra else "", d["cg_step"], results[0][2], ref["counter"], results[0][3], results[0][5], err), flush=True)
     os.environ.pop("MVTV_COMM", None)
     os.environ.pop("MVTV_FOLD_COMMIT", None)
+    for k in ("MVTV_STEP3D", "MVTV_STEP3D_CFG", "MVTV_INIT2D"):
+        os.environ.pop(k, None)
     print("emu_multi: %d failure(s)" % fail)
     return 1 if fail else 0
 
