@@ -54,10 +54,15 @@ extern "C" {
 
 /* x-update preconditioner for the matrix-free CG that replaces arma::spsolve (cpp-code/solvers.cpp:116) */
 #define MVTV_PRECOND_JACOBI 0 /* z = D^-1 r */
-#define MVTV_PRECOND_CHEB1 1  /* z = P(D^-1 M) D^-1 r, P = the degree-1 polynomial whose residual is the Chebyshev T2 on a
-                                 Gershgorin bound of spec(D^-1 M): one more stencil per CG iteration, ~1.9x fewer
-                                 iterations, ~1.5x less HBM traffic per solve; same solution to cg_rtol */
-#define MVTV_PRECOND_AUTO 2   /* CHEB1 when the previous x-update on this plan needed > 24 Jacobi-equivalent iterations */
+#define MVTV_PRECOND_CHEB1 1  /* z = P(D^-1 M) D^-1 r, P = the degree-1 polynomial whose residual is the Chebyshev T2 on
+                                 [b/30, b], b = a Gershgorin bound of spec(D^-1 M): one more stencil per CG iteration,
+                                 ~1.7x fewer iterations; same solution to cg_rtol */
+#define MVTV_PRECOND_AUTO 2   /* Jacobi while the previous x-update on this plan needed <= 24 Jacobi-equivalent iterations,
+                                 else the degree measured fastest for the plan's kernels (3 on one GPU with 2-D / 3-D
+                                 meshes of even m[0], 1 otherwise) */
+#define MVTV_PRECOND_CHEB2 3  /* degree 2..4 of the same Chebyshev family, evaluated in Horner form (one stencil pass per  */
+#define MVTV_PRECOND_CHEB3 4  /* degree): ~2.5x / 3.2x / 3.9x fewer iterations than Jacobi on 4096^2.  Plans whose kernels do */
+#define MVTV_PRECOND_CHEB4 5  /* not implement the degree (several GPUs, 4-D, odd m[0]) use the highest one they have.      */
 
 /* flags for mvtv_solve */
 #define MVTV_WARM_THETA_FROM_PLAN 1u /* theta_init ignored: continue from the theta left on the device */
@@ -146,9 +151,11 @@ int mvtv_plan_set_points_strided(mvtv_plan *plan, int64_t n, const double *data,
 /* Same with inputs already resident in HBM (device pointers on the plan's device). */
 int mvtv_plan_set_points_dev(mvtv_plan *plan, int64_t n, const double *data_colmajor_dev,
                              const double *y_dev, const double *axes_dev);
-/* Which kernels this plan runs, as a small JSON object (zu: k_zu_march | k_zu; cg_step / cg_prec: k_cg_step |
- * k_cg_step2d; cg_prec_words: words of HBM traffic per vertex of the preconditioner kernel; collectives: none | peer |
- * nccl).  bench.py uses it for the algorithmic bytes of each kernel class. */
+/* Which kernels this plan runs, as a small JSON object (zu: k_zu_march | k_zu; cg_step: k_cg_step | k_cg_step2d |
+ * k_cg_step3d; cg_prec_words: words of HBM traffic per vertex of the first preconditioner pass; fused_update: 1 when
+ * k_cg_update and the first preconditioner pass are one kernel; max_degree / auto_degree: polynomial degrees the plan
+ * implements / MVTV_PRECOND_AUTO picks; last_degree: degree of the latest x-update; collectives: none | peer | nccl).
+ * bench.py uses it for the algorithmic bytes of each kernel class. */
 int mvtv_plan_describe(const mvtv_plan *plan, char *buf, int64_t cap);
 /* Per-kernel-class CUDA-event timing on the plan's stream (used by bench.py for the roofline).
  * ms[k], count[k], k = MVTV_KC_*: accumulated milliseconds and number of launches since enable. */
@@ -156,8 +163,8 @@ int mvtv_plan_describe(const mvtv_plan *plan, char *buf, int64_t cap);
 #define MVTV_KC_ZU_INIT 1   /* same kernel, initial D^T D theta / D^T u pass */
 #define MVTV_KC_CG_INIT 2   /* b, r = b - M theta, p */
 #define MVTV_KC_CG_STEP 3   /* p = z + beta p fused with q = M p, p.q */
-#define MVTV_KC_CG_UPDATE 4 /* theta, r update, r.z, r.r */
-#define MVTV_KC_CG_PREC 5   /* MVTV_PRECOND_CHEB1: z = P(D^-1 M) D^-1 r, r.z */
+#define MVTV_KC_CG_UPDATE 4 /* theta, r update, r.z, r.r (fused_update: + the first preconditioner pass) */
+#define MVTV_KC_CG_PREC 5   /* polynomial preconditioner passes not fused into the update: z = P(D^-1 M) D^-1 r, r.z */
 #define MVTV_KC_N 8
 int mvtv_plan_profile(mvtv_plan *plan, int enable);
 int mvtv_plan_get_profile(mvtv_plan *plan, double *ms, int64_t *count);

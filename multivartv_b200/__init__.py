@@ -5,7 +5,8 @@ The numerical work lives in ``lib/libmvtv_b200.so`` (hand-written CUDA behind th
 Importing the package does not load the library; the first call does, and fails loudly if it is missing.
 """
 from . import _lib  # noqa: F401
-from ._lib import (F32, F64, MODE_CPP, MODE_PY, MODE_RCPP, PRECOND_AUTO, PRECOND_CHEB1, PRECOND_JACOBI, VARIANT_INTENDED,  # noqa: F401
+from ._lib import (F32, F64, MODE_CPP, MODE_PY, MODE_RCPP, PRECOND_AUTO, PRECOND_CHEB1, PRECOND_CHEB2, PRECOND_CHEB3, PRECOND_CHEB4,  # noqa: F401
+                   PRECOND_JACOBI, VARIANT_INTENDED,
                    VARIANT_REFERENCE, WARM_THETA_FROM_PLAN, WARM_U_FROM_PLAN, MvtvError, NotConverged)
 from .solvers import (Plan, adapt_step, axes_from_mesh, create_deltas, create_lambdas, create_mesh, kfoldinds, mbs, mbs_mse,  # noqa: F401
                       mbs_one, mbs_predict,

@@ -14,7 +14,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOT_CONVERGED, ERR_DIM_MISMATCH, ERR_UNSUPPORTED,
 MODE_CPP, MODE_RCPP, MODE_PY = 0, 1, 2
 VARIANT_REFERENCE, VARIANT_INTENDED = 0, 1
 F64, F32 = 64, 32
-PRECOND_JACOBI, PRECOND_CHEB1, PRECOND_AUTO = 0, 1, 2
+PRECOND_JACOBI, PRECOND_CHEB1, PRECOND_AUTO, PRECOND_CHEB2, PRECOND_CHEB3, PRECOND_CHEB4 = 0, 1, 2, 3, 4, 5
 WARM_THETA_FROM_PLAN, WARM_U_FROM_PLAN = 1, 2
 KC_NAMES = ["zu", "zu_init", "cg_init", "cg_step", "cg_update", "cg_prec"]
 KC_N = 8

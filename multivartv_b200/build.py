@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvtv_b200.so")
 SOURCES = ["solver.cu", "setup.cu"]
-HEADERS = ["kernels.cuh", "zu_march.cuh", "cg_step2d.cuh", "cg_step3d.cuh", "cg_step3dh.cuh", "cg_fused2d.cuh", "cg_init2d.cuh", "cg_horner2d.cuh", "mvtv_internal.cuh", "setup.h", os.path.join("..", "..", "include", "mvtv.h")]
+HEADERS = ["kernels.cuh", "zu_march.cuh", "cg_step2d.cuh", "cg_step3d.cuh", "cg_fused2d.cuh", "cg_init2d.cuh", "cg_horner2d.cuh", "mvtv_internal.cuh", "setup.h", os.path.join("..", "..", "include", "mvtv.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -24,15 +24,16 @@ struct Fused2dCfg {
 
 template <typename T, typename Cfg>
 __global__ void __launch_bounds__(Cfg::NT, (Cfg::MINB > 0 ? Cfg::MINB : 1))
-k_cg_updprec2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a, T *rbuf0, T *rbuf1,
+k_cg_updprec2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
                const RedBuf rb, const int zchunk) {
   if (cg_done(a.S, a.rtol2)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int it = (int)a.S[CS_ITERS];
   const int cur = it & 1;
   const T alpha = (T)(a.S[2 * cur] / a.S[CS_PQ]);
-  const T *__restrict__ r_in = cur ? rbuf1 : rbuf0;
-  T *__restrict__ r_out = cur ? rbuf0 : rbuf1;
+  const T *__restrict__ r_in = cur ? a.r2 : a.r;     // cg_rcur
+  T *__restrict__ r_out = cur ? a.r : a.r2;
+  T *__restrict__ zo = a.w_out_scr ? cg_wscratch(a, it, true) : a.z;   // first Horner pass of a degree >= 2 polynomial
   const T *__restrict__ p = a.pbuf[cur ^ 1];          // the direction k_cg_step2d<STEP_Z> just wrote
   const T *__restrict__ q = a.q;
   const T *__restrict__ dinv = a.dinv;
@@ -124,7 +125,7 @@ k_cg_updprec2d(const __grid_constant__ DimTab dt, const __grid_constant__ Stenci
         outv[k] = zv;
         red[0] += (double)rcp[k] * (double)zv;
       }
-      st2(a.z + (long long)zz * dt.plane + xx, outv[0], outv[1]);   // row zz-1 sits at (zz-1+1)*plane
+      st2(zo + (long long)zz * dt.plane + xx, outv[0], outv[1]);   // row zz-1 sits at (zz-1+1)*plane
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -137,7 +138,11 @@ k_cg_updprec2d(const __grid_constant__ DimTab dt, const __grid_constant__ Stenci
     }
   }
   double *S = a.S;
-  grid_reduce<2, 2>(red, rb, [S](const double (&res)[2]) { cg_commit_update(S, res); });
+  const int fin = a.final_pass;
+  grid_reduce<2, 2>(red, rb, [S, fin](const double (&res)[2]) {
+    if (fin) cg_commit_update(S, res);
+    else cg_commit_update_prec(S, res + 1);   // degree >= 2: r.z comes from the last Horner pass
+  });
 }
 
 }  // namespace mvtv

@@ -18,11 +18,16 @@ namespace mvtv {
 
 template <typename T, int WARPS, int MINB, bool FIRST>
 __global__ void __launch_bounds__(32 * WARPS, (MINB > 0 ? MINB : 1))
-k_cg_horner2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a, const T *w_in, T *w_out,
-              const double c_lo, const double c_hi, const int final_pass, const RedBuf rb, const int zchunk) {
+k_cg_horner2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
+              const RedBuf rb, const int zchunk) {
   if (cg_done(a.S, a.rtol2)) return;
+  const int it = (int)a.S[CS_ITERS];
+  const T *__restrict__ w_in = a.w_in_scr ? cg_wscratch(a, it, false) : a.z;
+  T *__restrict__ w_out = a.w_out_scr ? cg_wscratch(a, it, false) : a.z;
+  const double c_lo = a.pc0, c_hi = a.pc1;
+  const int final_pass = a.final_pass;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const T *__restrict__ r = a.r;
+  const T *__restrict__ r = cg_rcur(a, it);
   const T *__restrict__ dinv = a.dinv;
   const T rhoM = (T)a.rhoM;
   const int m0 = (int)dt.m[0];                        // even, >= 2
@@ -112,10 +117,9 @@ k_cg_horner2d(const __grid_constant__ DimTab dt, const __grid_constant__ Stencil
       rcp[k] = rown[k];
     }
   }
+  if (!final_pass) return;
   double *S = a.S;
-  grid_reduce<1, 1>(red, rb, [S, final_pass](const double (&res)[1]) {
-    if (final_pass) cg_commit_rz(S, res);
-  });
+  grid_reduce<1, 1>(red, rb, [S](const double (&res)[1]) { cg_commit_rz(S, res); });
 }
 
 // coefficients c_0 .. c_d of P with 1 - t P(t) = T_{d+1}((theta - t)/delta) / T_{d+1}(theta/delta) on [bmax/kappa, bmax]

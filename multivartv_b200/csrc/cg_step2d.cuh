@@ -68,7 +68,8 @@ k_cg_step2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   const T beta = first ? T(0) : (T)(a.S[2 * cur] / a.S[2 * (cur ^ 1)]);
   const T *__restrict__ p_in = a.pbuf[cur];
   T *__restrict__ p_out = a.pbuf[cur ^ 1];
-  const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : a.r;
+  const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : cg_rcur(a, it);
+  T *__restrict__ zo = a.w_out_scr ? cg_wscratch(a, it, false) : a.z;   // STEP_PREC output (first Horner pass of a degree >= 2 polynomial)
   const T *__restrict__ dinv = a.dinv;
   const T rhoM = (T)a.rhoM;
 
@@ -227,7 +228,7 @@ k_cg_step2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
           for (int g = 0; g < NG; ++g)
             if (valid[g]) {
               if (MODE == STEP_PREC) {
-                st2(a.z + ob + 2 * g, outv[2 * g], outv[2 * g + 1]);
+                st2(zo + ob + 2 * g, outv[2 * g], outv[2 * g + 1]);
                 if (a.peer) {  // fill the neighbours' ghost rows of z
                   if (zz - 1 == 0 && dt.has_lo) { st2((T *)a.peer->zghost_at_prev + x + 2 * g, outv[2 * g], outv[2 * g + 1]); __threadfence_system(); }
                   if (zz - 1 == dt.nz - 1 && dt.has_hi) { st2((T *)a.peer->zghost_at_next + x + 2 * g, outv[2 * g], outv[2 * g + 1]); __threadfence_system(); }
@@ -254,6 +255,7 @@ k_cg_step2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   const PeerTab *peer = a.peer;
   const unsigned long long sr = a.seq_red, sz = a.seq_zhalo;
   const int fold = a.fold;
+  if (MODE == STEP_PREC && !a.final_pass) return;    // first pass of a degree >= 2 polynomial (one GPU): r.z comes from the last pass
   grid_reduce<1, 1>(red, rb, [S, raw, peer, sr, sz, fold](const double (&res)[1]) {
     if (peer) {
       if (MODE == STEP_PREC) {

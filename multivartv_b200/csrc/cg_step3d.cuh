@@ -1,7 +1,11 @@
-// k_cg_step3d: the shared-memory-free variant of k_cg_step for 3-D meshes (EXPERIMENTAL: opt-in with MVTV_STEP3D=shfl,
-// written after round 1's GPU minutes were spent -- compiled for sm_100a but NOT yet run on a GPU; the default 3-D path
-// stays k_cg_step).  Same three modes, arguments, reduction epilogue and ghost-plane protocol as k_cg_step /
-// k_cg_step2d (cg_step2d.cuh, whose 2-D form is measured: 0.92 of the HBM peak for STEP_Z).
+// k_cg_step3d: the shared-memory-free CG kernels for 3-D meshes with an even m0 (the default there; measured on 512^3:
+// STEP_Z 1.02 ms = 0.81 of the HBM peak against 1.12 ms for the shared-memory ring of k_cg_step, STEP_PREC 0.78 against
+// 1.02 ms, profiles/r2_call1_step3d_probe.log).  Same modes, arguments, reduction epilogue and ghost-plane protocol as
+// k_cg_step / k_cg_step2d, plus the two modes of the polynomial preconditioner of degree >= 2 and of the fused update:
+//   STEP_HORNER   w_out = D^-1 M w_in + pc0 * D^-1 r          (pass k >= 2 of the Horner form; reads w_in, dinv, r: 4 N words)
+//   STEP_UPDPREC  theta += alpha p ; r_new = r - alpha q (out of place) ; w_out = pc0 z0 + pc1 D^-1 M z0, z0 = D^-1 r_new
+//                 (k_cg_update fused with the first preconditioner pass: reads theta, p, r, q, dinv, writes theta, r, w:
+//                 8 N words instead of 6 N + 3 N; r_new is also formed on the halo rows / planes, which needs q there)
 //
 // A warp owns 64 consecutive vertices of axis 0 (two per lane, 16-byte accesses) times RY consecutive rows of axis 1 and
 // marches along axis 2.  Per plane a lane loads its pair on RY + 2 rows (the two extra rows are the clamped y-neighbours:
@@ -26,15 +30,24 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
             const RedBuf rb, const int zchunk) {
   if (cg_done(a.S, a.rtol2)) return;
   constexpr int RY = Cfg::RY, NR = Cfg::RY + 2;
-  constexpr bool NOC = Cfg::NOC && (MODE == STEP_PREC);
+  constexpr bool POLY = (MODE == STEP_PREC || MODE == STEP_HORNER || MODE == STEP_UPDPREC);   // writes a preconditioner pass
+  constexpr bool NOC = (Cfg::NOC && MODE == STEP_PREC) || MODE == STEP_HORNER || MODE == STEP_UPDPREC;
+  constexpr bool STAGE_B = (MODE == STEP_JACOBI || MODE == STEP_PREC || MODE == STEP_UPDPREC);   // dinv on all loaded rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int it = (int)a.S[CS_ITERS];
   const int cur = it & 1;
-  const bool first = (MODE == STEP_PREC) ? true : (it == 0);   // "first": no p_old term
+  const bool first = POLY ? true : (it == 0);   // "first": no p_old term
+  const bool stage_c = (MODE == STEP_UPDPREC) || !first;   // third staged array: p_old (JACOBI, Z) or q (UPDPREC)
   const T beta = first ? T(0) : (T)(a.S[2 * cur] / a.S[2 * (cur ^ 1)]);
-  const T *__restrict__ p_in = a.pbuf[cur];
+  const T alpha = (MODE == STEP_UPDPREC) ? (T)(a.S[2 * cur] / a.S[CS_PQ]) : T(0);
+  const T *__restrict__ p_in = (MODE == STEP_UPDPREC) ? a.q : a.pbuf[cur];
   T *__restrict__ p_out = a.pbuf[cur ^ 1];
-  const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : a.r;
+  const T *__restrict__ rcur = cg_rcur(a, it);
+  const T *__restrict__ w_in = a.w_in_scr ? cg_wscratch(a, it, false) : a.z;
+  const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : ((MODE == STEP_HORNER) ? w_in : rcur);
+  T *__restrict__ r_out = (MODE == STEP_UPDPREC) ? (cur ? a.r : a.r2) : nullptr;
+  const T *__restrict__ p_dir = a.pbuf[cur ^ 1];   // STEP_UPDPREC: the direction the step kernel just wrote
+  T *__restrict__ zo = a.w_out_scr ? cg_wscratch(a, it, MODE == STEP_UPDPREC) : a.z;
   const T *__restrict__ dinv = a.dinv;
   const T rhoM = (T)a.rhoM;
 
@@ -84,14 +97,15 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
       cls[j][k] = ((x + k == 0 || x + k == m0 - 1) ? 1 : 0) | ((y0 + j == 0 || y0 + j == m1 - 1) ? 2 : 0);
 
   // raw inputs of the next plane, in flight while the current one is consumed
-  T ra[NR][2], rb_[NR][2], rc[NR][2], rcc[RY][2], ha[NR], hb[NR], hc[NR];
+  // rcc / rdd: own-row extras -- diag(c) (!NOC) ; dinv and r (STEP_HORNER) ; theta and p (STEP_UPDPREC)
+  T ra[NR][2], rb_[NR][2], rc[NR][2], rcc[RY][2], rdd[RY][2], ha[NR], hb[NR], hc[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     ra[r][0] = ra[r][1] = rb_[r][0] = rb_[r][1] = rc[r][0] = rc[r][1] = T(0);
     ha[r] = hb[r] = hc[r] = T(0);
   }
 #pragma unroll
-  for (int j = 0; j < RY; ++j) rcc[j][0] = rcc[j][1] = T(0);
+  for (int j = 0; j < RY; ++j) rcc[j][0] = rcc[j][1] = rdd[j][0] = rdd[j][1] = T(0);
   auto load_plane = [&](int zz) {
     if (zz > zlast) return;
     const int zs = min(max(zz, zlo), zhi);
@@ -99,18 +113,23 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       ld2(rr + pb + rowoff[r], ra[r]);
-      if (MODE != STEP_Z) ld2(dinv + pb + rowoff[r], rb_[r]);
-      if (!first) ld2(p_in + pb + rowoff[r], rc[r]);
+      if (STAGE_B) ld2(dinv + pb + rowoff[r], rb_[r]);
+      if (stage_c) ld2(p_in + pb + rowoff[r], rc[r]);
       if (edge) {
         ha[r] = rr[pb + rowoff_h[r]];
-        if (MODE != STEP_Z) hb[r] = dinv[pb + rowoff_h[r]];
-        if (!first) hc[r] = p_in[pb + rowoff_h[r]];
+        if (STAGE_B) hb[r] = dinv[pb + rowoff_h[r]];
+        if (stage_c) hc[r] = p_in[pb + rowoff_h[r]];
       }
     }
-    if (!NOC && zz >= zc0 && zz < zc1) {
+    if (zz >= zc0 && zz < zc1) {
 #pragma unroll
       for (int j = 0; j < RY; ++j)
-        if (valid[j]) ld2(a.c + (long long)(zz + 1) * dt.plane + (long long)(y0 + j) * m0 + x, rcc[j]);
+        if (valid[j]) {
+          const long long ob = (long long)(zz + 1) * dt.plane + (long long)(y0 + j) * m0 + x;
+          if (!NOC) ld2(a.c + ob, rcc[j]);
+          if (MODE == STEP_HORNER) { ld2(dinv + ob, rcc[j]); ld2(rcur + ob, rdd[j]); }
+          if (MODE == STEP_UPDPREC) { ld2(a.x + ob, rcc[j]); ld2(p_dir + ob, rdd[j]); }
+        }
     }
   };
 
@@ -119,36 +138,54 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   for (int j = 0; j < RY; ++j)
 #pragma unroll
     for (int k = 0; k < 2; ++k) A0[j][k] = A1[j][k] = A2[j][k] = pcp[j][k] = cqp[j][k] = rcp[j][k] = dcp[j][k] = T(0);
-  double red[1] = {0.0};
+  double red[2] = {0.0, 0.0};   // [1]: r.r of STEP_UPDPREC
 
   load_plane(zfirst);
   for (int zz = zfirst; zz <= zlast; ++zz) {
-    // ---- combine: p_new of plane zz on the RY+2 rows, at the pair and at the strip's halo element
+    // ---- combine: p_new (z0, w) of plane zz on the RY+2 rows, at the pair and at the strip's halo element
     T v[NR][2], hv[NR], rown[RY][2], down[RY][2], cown[RY][2];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        v[r][k] = (MODE == STEP_Z) ? ra[r][k] : rb_[r][k] * ra[r][k];
-        if (!first) v[r][k] += beta * rc[r][k];
+        if (MODE == STEP_UPDPREC) {
+          ra[r][k] -= alpha * rc[r][k];                  // r_new = r - alpha q
+          v[r][k] = rb_[r][k] * ra[r][k];
+        } else {
+          v[r][k] = STAGE_B ? rb_[r][k] * ra[r][k] : ra[r][k];
+          if (!first) v[r][k] += beta * rc[r][k];
+        }
       }
-      hv[r] = (MODE == STEP_Z) ? ha[r] : hb[r] * ha[r];
-      if (!first) hv[r] += beta * hc[r];
+      if (MODE == STEP_UPDPREC) hv[r] = hb[r] * (ha[r] - alpha * hc[r]);
+      else {
+        hv[r] = STAGE_B ? hb[r] * ha[r] : ha[r];
+        if (!first) hv[r] += beta * hc[r];
+      }
       if (!xvalid) v[r][0] = v[r][1];                    // replicate vertex m0-1
     }
 #pragma unroll
     for (int j = 0; j < RY; ++j)
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        rown[j][k] = ra[j + 1][k];
-        down[j][k] = rb_[j + 1][k];
+        rown[j][k] = (MODE == STEP_HORNER) ? rdd[j][k] : ra[j + 1][k];
+        down[j][k] = (MODE == STEP_HORNER) ? rcc[j][k] : rb_[j + 1][k];
         cown[j][k] = rcc[j][k];
       }
+    if (MODE == STEP_UPDPREC && zz >= zc0 && zz < zc1) {   // theta and r_new of the own rows of an own plane
+#pragma unroll
+      for (int j = 0; j < RY; ++j)
+        if (valid[j]) {
+          const long long ob = (long long)(zz + 1) * dt.plane + (long long)(y0 + j) * m0 + x;
+          st2(r_out + ob, ra[j + 1][0], ra[j + 1][1]);
+          st2(a.x + ob, rcc[j][0] + alpha * rdd[j][0], rcc[j][1] + alpha * rdd[j][1]);
+          red[1] += (double)ra[j + 1][0] * (double)ra[j + 1][0] + (double)ra[j + 1][1] * (double)ra[j + 1][1];
+        }
+    }
     load_plane(zz + 1);                                  // the registers are free: the next plane goes in flight
     {
       const int zs = min(max(zz, zlo), zhi);
       const bool own = (zz == zs) && ((zz >= zc0 && zz < zc1) || (zz < 0 && zc0 == 0) || (zz >= dt.nz && zc1 == dt.nz));
-      if (MODE != STEP_PREC && own) {
+      if (!POLY && own) {
 #pragma unroll
         for (int j = 0; j < RY; ++j)
           if (valid[j]) st2(p_out + (long long)(zs + 1) * dt.plane + (long long)(y0 + j) * m0 + x, v[j + 1][0], v[j + 1][1]);
@@ -191,7 +228,12 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const T pv = pcp[j][k];
-          if (MODE == STEP_PREC) {
+          if (MODE == STEP_HORNER) {   // w_k = D^-1 M w_{k-1} + pc0 z0,  D^-1 M w = w + dinv*rhoM*(K w - diag(K) w)
+            const T dk = (T)st.diagK[cls[j][k] | bz];
+            const T zv = pv + rhoM * dcp[j][k] * (A0[j][k] - dk * pv) + (T)a.pc0 * (dcp[j][k] * rcp[j][k]);
+            outv[k] = zv;
+            red[0] += (double)rcp[j][k] * (double)zv;
+          } else if (POLY) {
             T zv;
             if (NOC) {   // dinv*q = z0 + dinv*rhoM*(K z0 - diag(K) z0): diag(c) never read
               const T dk = (T)st.diagK[cls[j][k] | bz];
@@ -208,9 +250,9 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
             red[0] += (double)pv * (double)qv;
           }
         }
-        if (MODE == STEP_PREC) {
-          st2(a.z + ob, outv[0], outv[1]);
-          if (a.peer) {  // fill the neighbours' ghost planes of z
+        if (POLY) {
+          st2(zo + ob, outv[0], outv[1]);
+          if (MODE == STEP_PREC && a.peer) {  // fill the neighbours' ghost planes of z
             const long long q = (long long)(y0 + j) * m0 + x;
             if (zz - 1 == 0 && dt.has_lo) { st2((T *)a.peer->zghost_at_prev + q, outv[0], outv[1]); __threadfence_system(); }
             if (zz - 1 == dt.nz - 1 && dt.has_hi) { st2((T *)a.peer->zghost_at_next + q, outv[0], outv[1]); __threadfence_system(); }
@@ -237,7 +279,22 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   const PeerTab *peer = a.peer;
   const unsigned long long sr = a.seq_red, sz = a.seq_zhalo;
   const int fold = a.fold;
-  grid_reduce<1, 1>(red, rb, [S, raw, peer, sr, sz, fold](const double (&res)[1]) {
+  if (MODE == STEP_UPDPREC) {   // one GPU: {r.z, r.r} of the next parity, iteration count advances
+    const int fin = a.final_pass;
+    grid_reduce<2, 2>(red, rb, [S, fin](const double (&res)[2]) {
+      if (fin) cg_commit_update(S, res);
+      else cg_commit_update_prec(S, res + 1);   // r.z comes from the last Horner pass
+    });
+    return;
+  }
+  if (MODE == STEP_HORNER || (MODE == STEP_PREC && !a.final_pass)) {   // one GPU
+    if (!a.final_pass) return;
+    double r1[1] = {red[0]};
+    grid_reduce<1, 1>(r1, rb, [S](const double (&res)[1]) { cg_commit_rz(S, res); });
+    return;
+  }
+  double r1[1] = {red[0]};
+  grid_reduce<1, 1>(r1, rb, [S, raw, peer, sr, sz, fold](const double (&res)[1]) {
     if (peer) {
       if (MODE == STEP_PREC) {
         __threadfence_system();

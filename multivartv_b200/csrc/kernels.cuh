@@ -301,11 +301,29 @@ struct CgArgs {
   unsigned long long seq_halo;  // version of r's ghost planes this launch posts (init, update) or needs (step / prec)
   unsigned long long seq_zhalo; // version of z's ghost planes (polynomial preconditioner: prec posts, step needs)
   T *z;            // polynomial preconditioner: z = P(D^-1 M) D^-1 r (ghosted slab)
-  double pc0, pc1; // z = pc0*z0 + pc1*D^-1 M z0,  z0 = D^-1 r
-  int prec;        // 0: Jacobi (z = D^-1 r formed on the fly), 1: degree-1 Chebyshev polynomial in D^-1 M
+  double pc0, pc1; // first Horner pass: w_1 = pc0*z0 + pc1*D^-1 M z0,  z0 = D^-1 r  (degree 1: w_1 = z)
+  int prec;        // 0: Jacobi (z = D^-1 r formed on the fly), d >= 1: degree-d Chebyshev polynomial in D^-1 M
+  // degree >= 2 (Horner form, one stencil pass per degree): w ping-pongs between the z buffer and a scratch buffer, ending
+  // in z.  The scratch is the direction buffer that is idle between two step kernels -- pbuf[parity ^ 1] once the update has
+  // advanced the iteration count, pbuf[parity] inside the fused update (cg_wscratch) -- so q stays readable.
+  int w_out_scr = 0;         // this pass writes the scratch buffer (else z)
+  int w_in_scr = 0;          // pass k >= 2 reads w_{k-1} from the scratch buffer (else z):  w_k = D^-1 M w_{k-1} + pc0*z0
+  int final_pass = 1;        // the pass that produces z also reduces r.z
+  // fused update + first preconditioner pass (k_cg_updprec*): r is updated OUT OF PLACE, the buffer holding the
+  // current residual is selected by the parity of the iterations performed (r2 == nullptr: r is updated in place)
+  T *r2 = nullptr;
   int fold;        // peer path, EXPERIMENTAL (MVTV_FOLD_COMMIT=1): the reducing kernel's last thread also waits for the world's
                    // partials and commits the scalars, instead of a separate one-thread k_cg_peer_commit_* launch
 };
+
+// the idle direction buffer (see CgArgs::w_out_scr); before_commit: called by the kernel that advances the iteration count
+template <typename T>
+__device__ __forceinline__ T *cg_wscratch(const CgArgs<T> &a, int iters, bool before_commit) {
+  return a.pbuf[before_commit ? (iters & 1) : ((iters & 1) ^ 1)];
+}
+// the buffer holding the current residual (see CgArgs::r2)
+template <typename T>
+__device__ __forceinline__ T *cg_rcur(const CgArgs<T> &a, int iters) { return (a.r2 && (iters & 1)) ? a.r2 : a.r; }
 
 __device__ __forceinline__ bool cg_done(const double *S, double rtol2) {
   const int cur = ((int)S[CS_ITERS]) & 1;
@@ -481,7 +499,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   STEP_JACOBI  stage r, dinv, p_old : p = dinv.*r + beta*p_old ; writes p, q = M p ; reduces p.q
 //   STEP_Z       stage z, p_old       : p = z + beta*p_old       ; writes p, q = M p ; reduces p.q
 //   STEP_PREC    stage r, dinv        : z0 = dinv.*r ; writes z = pc0*z0 + pc1*dinv.*(M z0) ; reduces r.z
-enum { STEP_JACOBI = 0, STEP_Z = 1, STEP_PREC = 2 };
+enum { STEP_JACOBI = 0, STEP_Z = 1, STEP_PREC = 2, STEP_HORNER = 3, STEP_UPDPREC = 4 };   // the last two: cg_step3d.cuh
 
 template <typename T, typename Cfg, int MODE>
 __global__ void __launch_bounds__(Cfg::NT, (Cfg::NT <= 256 ? (MODE != STEP_PREC ? 4 : 3) : 1))
@@ -506,7 +524,8 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   const T beta = first ? T(0) : (T)(a.S[2 * cur] / a.S[2 * (cur ^ 1)]);
   const T *__restrict__ p_in = a.pbuf[cur];
   T *__restrict__ p_out = a.pbuf[cur ^ 1];
-  const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : a.r;     // first staged array
+  const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : cg_rcur(a, it);     // first staged array
+  T *__restrict__ zo = a.w_out_scr ? cg_wscratch(a, it, false) : a.z;     // STEP_PREC output
   const T *__restrict__ dinv = a.dinv;
   const T rhoM = (T)a.rhoM;
 
@@ -693,7 +712,7 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
             const T qv = cq0[i][j] * pv + rhoM * A0[i][j];
             if (MODE == STEP_PREC) {
               const T zv = (T)a.pc0 * pv + (T)a.pc1 * (dcp[i][j] * qv);
-              a.z[pb + oidx[i][j]] = zv;
+              zo[pb + oidx[i][j]] = zv;
               if (a.peer) {  // fill the neighbours' ghost planes of z
                 if (zz - 1 == 0 && dt.has_lo) { ((T *)a.peer->zghost_at_prev)[oidx[i][j]] = zv; __threadfence_system(); }
                 if (zz - 1 == dt.nz - 1 && dt.has_hi) { ((T *)a.peer->zghost_at_next)[oidx[i][j]] = zv; __threadfence_system(); }

@@ -16,7 +16,6 @@
 
 #include "cg_step2d.cuh"
 #include "cg_step3d.cuh"
-#include "cg_step3dh.cuh"
 #include "cg_fused2d.cuh"
 #include "cg_init2d.cuh"
 #include "cg_horner2d.cuh"
@@ -98,6 +97,8 @@ template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFlo
 
 using namespace mvtv;
 
+enum { CGF_RING = 0, CGF_STRIP2D = 1, CGF_STRIP3D = 2 };
+
 // ------------------------------------------------------------------------------------------------
 struct mvtv_plan {
   int p = 0;            // user-visible number of axes
@@ -147,28 +148,24 @@ struct mvtv_plan {
   long long vid_cap = 0;
   long long launches = 0;
   int last_cg_iters = 8;
-  int last_cg_prec = 0;
+  int last_cg_prec = 0;     // polynomial degree of the previous x-update (0 = Jacobi)
   // peer-memory collectives of the CG loop (CUDA IPC); falls back to NCCL when unavailable or MVTV_COMM=nccl
   unsigned char *cb = nullptr;          // this rank's comm buffer (slots, flags, halo flags, error word)
   PeerTab *d_peer = nullptr;            // device copy of the peer table, nullptr = NCCL path
-  bool fold_commit = false;             // peer path, EXPERIMENTAL (MVTV_FOLD_COMMIT=1): no separate commit launches
+  bool fold_commit = true;              // peer path: the reducing kernel's last thread commits the CG scalars (MVTV_FOLD_COMMIT=0: separate commit launches)
   std::vector<void *> ipc_opened;
   unsigned long long red_seq = 0, halo_seq = 0, zhalo_seq = 0;
   double cheb_bmax = 0.0;   // bound on the spectrum of D^-1 (diag(c) + s D^T D), independent of s and c
-  int step2d_cfg = 0, step2d_prec_cfg = 0;   // tile variants of k_cg_step2d (MVTV_STEP2D_CFG, MVTV_STEP2D_PREC_CFG)
-  int cheb_degree = 1;         // 2-D, one GPU: EXPERIMENTAL degree 2..4 polynomial preconditioner (MVTV_CHEB_DEGREE), default 1
-  double cheb_kappa = 30.0;    // the polynomial is the Chebyshev one on [bmax/kappa, bmax] (MVTV_CHEB_KAPPA)
-  double cheb1_kappa = 30.0;   // interval of the degree-1 polynomial (MVTV_CHEB1_KAPPA; the measured default is 30)
-  int horner_cfg = 0;          // MVTV_HORNER_CFG: 0 = 4 CTAs of 256 threads per SM (64 registers, 8..40 bytes spilled), 1 = 3 CTAs (85 registers)
-  bool init2d = false;         // 2-D: EXPERIMENTAL marching k_cg_init2d (MVTV_INIT2D=1), default off
-  bool fuse_updprec = false;   // 2-D, one GPU: EXPERIMENTAL k_cg_updprec2d (MVTV_FUSE_UPDPREC=1), default off
-  int fuse_cfg = 0;
-  void *r2 = nullptr;          // second residual buffer of the fused kernel (allocated on first use)
-  bool step3d = false;   // 3-D meshes: EXPERIMENTAL shuffle-based k_cg_step3d (MVTV_STEP3D=shfl), default off
-  bool step3dh = false;  // 3-D meshes: EXPERIMENTAL hybrid k_cg_step3dh (MVTV_STEP3D=hyb), default off
-  int step3d_cfg = 0;
-  bool step2d = false;   // 2-D meshes: shuffle-based k_cg_step2d (cg_step2d.cuh) instead of the shared-memory k_cg_step
-  int zu_cfg = 0;        // tile variant of k_zu_march (MVTV_ZU_CFG), 0 = default
+  double cheb_kappa = 30.0; // the polynomial preconditioner is the Chebyshev one on [bmax/kappa, bmax]
+  // which kernels run the stencil passes of the CG loop (decided once per plan from the mesh):
+  //   CGF_STRIP2D / CGF_STRIP3D  shuffle-based marching kernels (cg_step2d.cuh / cg_step3d.cuh): 2-D / 3-D meshes with an even m0
+  //   CGF_RING                   shared-memory ring k_cg_step (kernels.cuh): everything else (4-D, odd m0); MVTV_STEP=ring forces it
+  int cg_family = 0;
+  int max_degree = 1;       // highest polynomial degree this plan's kernels implement
+  int auto_degree = 1;      // what MVTV_PRECOND_AUTO picks once Jacobi needs more than 24 iterations (measured per family)
+  bool fused_update = false;   // one GPU, strip kernels: k_cg_update fused with the first preconditioner pass (r out of place)
+  int tune_fuse3d = 0, tune_horner3d = 0;   // developer knob MVTV_TUNE: tile candidates still being measured
+  void *r2 = nullptr;          // second residual buffer of the fused update (allocated on first use)
   int zu_variant = -1;   // ZV_* when the compile-time block tables of k_zu_march match this plan, else -1 (gather kernel)
 
   // optional per-kernel-class CUDA-event timing on the plan's stream (mvtv_plan_profile)
@@ -342,40 +339,42 @@ struct mvtv_plan {
       for (int b = 0; same && b < K; ++b) same = (zu_block_mask(P, V, b) == bt.mask[b]);
       const char *env = getenv("MVTV_ZU_KERNEL");
       zu_variant = (same && !(env && std::string(env) == "gather")) ? V : -1;
-      const char *zc = getenv("MVTV_ZU_CFG");
-      zu_cfg = zc ? atoi(zc) : 0;
     }
 
     {
-      const char *env = getenv("MVTV_STEP2D");
-      const bool want = !(env && std::string(env) == "smem");   // MVTV_STEP2D=smem forces the shared-memory k_cg_step
-      step2d = want && P == 2 && (m[0] % 2 == 0) && m[0] >= 2;
-      const char *c2 = getenv("MVTV_STEP2D_CFG");
-      step2d_cfg = c2 ? atoi(c2) : 0;
-      const char *c3 = getenv("MVTV_STEP2D_PREC_CFG");
-      step2d_prec_cfg = c3 ? atoi(c3) : 0;
-      const char *ed = getenv("MVTV_CHEB_DEGREE");
-      cheb_degree = ed ? std::max(1, std::min(4, atoi(ed))) : 1;
-      if (!(step2d && world == 1)) cheb_degree = 1;
-      const char *ek = getenv("MVTV_CHEB_KAPPA");
-      cheb_kappa = ek ? std::max(2.0, atof(ek)) : 30.0;
+      const char *env = getenv("MVTV_STEP");
+      const bool ring = env && std::string(env) == "ring";   // MVTV_STEP=ring: the shared-memory k_cg_step everywhere (cross-checks)
+      const bool even = (m[0] % 2 == 0) && m[0] >= 2;
+      cg_family = (!ring && even && P == 2) ? CGF_STRIP2D : ((!ring && even && P == 3) ? CGF_STRIP3D : CGF_RING);
+      // Horner passes of degree >= 2 and the fused update exist in the strip kernels, on one GPU (their halo rows need q / w
+      // of the neighbour rank, which the peer protocol does not exchange)
+      const bool strip1 = (cg_family != CGF_RING) && world == 1;
+      max_degree = strip1 ? 4 : 1;
+      auto_degree = strip1 ? 3 : 1;
+      fused_update = strip1;
       const char *efc = getenv("MVTV_FOLD_COMMIT");
-      fold_commit = efc && std::string(efc) == "1";
-      const char *e1 = getenv("MVTV_CHEB1_KAPPA");
-      cheb1_kappa = e1 ? std::max(2.0, atof(e1)) : 30.0;
-      const char *eh = getenv("MVTV_HORNER_CFG");
-      horner_cfg = eh ? atoi(eh) : 0;
-      const char *ei = getenv("MVTV_INIT2D");
-      init2d = ei && std::string(ei) == "1" && step2d;
-      const char *ef = getenv("MVTV_FUSE_UPDPREC");
-      fuse_updprec = ef && std::string(ef) == "1" && step2d && world == 1;
-      const char *cf = getenv("MVTV_FUSE_CFG");
-      fuse_cfg = cf ? atoi(cf) : 0;
-      const char *e3 = getenv("MVTV_STEP3D");
-      step3d = e3 && std::string(e3) == "shfl" && P == 3 && (m[0] % 2 == 0) && m[0] >= 2;
-      step3dh = e3 && std::string(e3) == "hyb" && P == 3 && (m[0] % 2 == 0) && m[0] >= 2;
-      const char *c4 = getenv("MVTV_STEP3D_CFG");
-      step3d_cfg = c4 ? atoi(c4) : 0;
+      fold_commit = !(efc && std::string(efc) == "0");
+      // MVTV_TUNE="key=value,...": developer knob for A/B measurements of candidates that are still compiled in
+      // (fused=0|1, degree=1..4 for MVTV_PRECOND_AUTO, fuse3d / horner3d = tile candidate)
+      if (const char *tune = getenv("MVTV_TUNE")) {
+        std::string t(tune);
+        size_t pos = 0;
+        while (pos < t.size()) {
+          size_t end = t.find(',', pos);
+          if (end == std::string::npos) end = t.size();
+          const std::string kv = t.substr(pos, end - pos);
+          const size_t eq = kv.find('=');
+          if (eq != std::string::npos) {
+            const std::string k = kv.substr(0, eq);
+            const int v = atoi(kv.c_str() + eq + 1);
+            if (k == "fused") fused_update = fused_update && v != 0;
+            else if (k == "degree") auto_degree = std::max(1, std::min(v, max_degree));
+            else if (k == "fuse3d") tune_fuse3d = v;
+            else if (k == "horner3d") tune_horner3d = v;
+          }
+          pos = end + 1;
+        }
+      }
     }
 
     // 3^P-point stencil of D^T D = sum_b c_b^2 kron_{a in S'_b} L_a  (SURVEY A.6), clamped indices
@@ -589,7 +588,8 @@ struct mvtv_plan {
   void set_points_t(long long npts, const double *data_dev, long long ld_point, long long ld_axis,
                     const double *y_dev, const double *axes_dev) {
     use_device();
-    MVTV_REQUIRE(npts >= 1 && npts < (1ll << 31), "n must be in [1, 2^31)");
+    // world > 1: a rank whose slab holds no points (clustered data, strong scaling) still takes part in every collective
+    MVTV_REQUIRE(npts >= (world > 1 ? 0 : 1) && npts < (1ll << 31), "n must be in [1, 2^31)");
     if (npts > vid_cap) {
       if (vid) MVTV_CUDA(cudaFree(vid));
       vid = nullptr;
@@ -598,28 +598,34 @@ struct mvtv_plan {
       vid_cap = npts;
     }
     have_points = false;   // a failure below must not leave a half-built operator behind
-    const size_t tb = sort_temp_bytes(npts);
-    const size_t kb = (sizeof(unsigned) * (size_t)npts * 4 + 255) & ~(size_t)255;
-    unsigned *key_in = (unsigned *)grow(sort_buf, sort_bytes, kb + std::max<size_t>(tb, 16));
-    unsigned *key_out = key_in + npts, *val_in = key_out + npts, *val_out = val_in + npts;
-    void *temp = (unsigned char *)key_in + kb;
-    launch_bin(p, dt, npts, data_dev, ld_point, ld_axis, axes_dev, vid, key_in, val_in, stream);
-    launch_sort(temp, tb, npts, key_in, key_out, val_in, val_out, stream);
     const size_t vb = (size_t)dt.usz * esz();
     MVTV_CUDA(cudaMemsetAsync(oty, 0, vb, stream));
     MVTV_CUDA(cudaMemsetAsync(cnt, 0, vb, stream));
-    launch_segment_reduce<T>(npts, key_out, val_out, y_dev, dt.plane, (T *)oty, (T *)cnt, stream);
-    launches += 5;
-    // mean(y) (cpp-code/solvers.cpp:95,103): deterministic two-level sum on the device
-    sum_y(y_dev, npts);
-    MVTV_CUDA(cudaStreamSynchronize(stream));
-    if (world > 1) {
-      // every rank must hold exactly the points of its own slab (partition.exchange_points)
-      unsigned last_key = 0;
-      MVTV_CUDA(cudaMemcpy(&last_key, key_out + (npts - 1), sizeof(unsigned), cudaMemcpyDeviceToHost));
-      if (last_key == 0xFFFFFFFFu)
-        throw Error(MVTV_ERR_INVALID, "world > 1: a point's nearest vertex lies outside this rank's slab");
+    double foreign = 0.0;
+    if (npts > 0) {
+      const size_t tb = sort_temp_bytes(npts);
+      const size_t kb = (sizeof(unsigned) * (size_t)npts * 4 + 255) & ~(size_t)255;
+      unsigned *key_in = (unsigned *)grow(sort_buf, sort_bytes, kb + std::max<size_t>(tb, 16));
+      unsigned *key_out = key_in + npts, *val_in = key_out + npts, *val_out = val_in + npts;
+      void *temp = (unsigned char *)key_in + kb;
+      launch_bin(p, dt, npts, data_dev, ld_point, ld_axis, axes_dev, vid, key_in, val_in, stream);
+      launch_sort(temp, tb, npts, key_in, key_out, val_in, val_out, stream);
+      launch_segment_reduce<T>(npts, key_out, val_out, y_dev, dt.plane, (T *)oty, (T *)cnt, stream);
+      launches += 3;
+      if (world > 1) {
+        // every rank must hold exactly the points of its own slab (partition.exchange_points); the verdict is
+        // all-reduced below so that no rank throws while its peers wait in a collective
+        unsigned last_key = 0;
+        MVTV_CUDA(cudaMemcpyAsync(&last_key, key_out + (npts - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        MVTV_CUDA(cudaStreamSynchronize(stream));
+        if (last_key == 0xFFFFFFFFu) foreign = 1.0;
+      }
     }
+    // mean(y) (cpp-code/solvers.cpp:95,103): deterministic two-level sum on the device; world > 1: the point count and the
+    // foreign-point flag ride on the same all-reduce
+    const double flagged = sum_y(y_dev, npts, foreign);
+    if (flagged != 0.0)
+      throw Error(MVTV_ERR_INVALID, "world > 1: a point's nearest vertex lies outside its rank's slab (on at least one rank)");
     exchange_ghosts<T>((T *)cnt);   // diag(c) on the ghost planes feeds the redundant ghost-plane work
     MVTV_CUDA(cudaStreamSynchronize(stream));
     dinv_rho = NAN;
@@ -627,7 +633,7 @@ struct mvtv_plan {
     have_points = true;
     have_u_state = have_theta_state = false;
   }
-  void sum_y(const double *y_dev, long long npts);
+  double sum_y(const double *y_dev, long long npts, double flag);
 
   // ---- the ADMM loop ---------------------------------------------------------------------------
   template <typename T, int P>
@@ -720,21 +726,27 @@ __global__ void __launch_bounds__(256) k_maxabs_D(const __grid_constant__ DimTab
   grid_reduce<1, 0>(red, rb, [out](const double (&res)[1]) { out[0] = res[0]; });
 }
 
-void mvtv_plan::sum_y(const double *y_dev, long long npts) {
+// returns the world-wide sum of `flag` (set_points' error word); sets mean_y
+double mvtv_plan::sum_y(const double *y_dev, long long npts, double flag) {
   const int g = std::min<int>(grid1d(npts), (int)nblocks);
   RedBuf rb{partials, counters + 4};
   k_sum<<<g, 256, 0, stream>>>(y_dev, npts, rb, zr);
   MVTV_CUDA(cudaGetLastError());
   launches += 1;
-  double cnt_total = (double)npts;
+  double extra[2] = {(double)npts, flag};
   if (world > 1) {  // global mean over the disjoint per-rank point sets
-    MVTV_CUDA(cudaMemcpyAsync(zr + 1, &cnt_total, sizeof(double), cudaMemcpyHostToDevice, stream));
-    allreduce(zr, 2, ncclSum);
+    MVTV_CUDA(cudaMemcpyAsync(zr + 1, extra, sizeof(double) * 2, cudaMemcpyHostToDevice, stream));
+    allreduce(zr, 3, ncclSum);
   }
-  MVTV_CUDA(cudaMemcpyAsync(h_scal, zr, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream));
+  MVTV_CUDA(cudaMemcpyAsync(h_scal, zr, sizeof(double) * 3, cudaMemcpyDeviceToHost, stream));
   MVTV_CUDA(cudaStreamSynchronize(stream));
-  if (world > 1) cnt_total = h_scal[1];
-  mean_y = h_scal[0] / cnt_total;
+  const double cnt_total = world > 1 ? h_scal[1] : (double)npts;
+  const double flagged = world > 1 ? h_scal[2] : flag;
+  if (flagged == 0.0) {
+    MVTV_REQUIRE(cnt_total >= 1.0, "no points on any rank");
+    mean_y = h_scal[0] / cnt_total;
+  }
+  return flagged;
 }
 
 template <typename T, typename Cfg, int V>
@@ -797,28 +809,12 @@ void mvtv_plan::launch_zu(double kappa, double usc, int mode, int init, bool wit
       case 2 * 4 + ZV_REFERENCE: launch_zu_march<T, ZuCfg<2, 256, 1, 1>, ZV_REFERENCE>(a, rb); done = true; break;
       case 2 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<2, 256, 1, 1>, ZV_INTENDED>(a, rb); done = true; break;
       case 2 * 4 + ZV_P1: launch_zu_march<T, ZuCfg<2, 256, 1, 1>, ZV_P1>(a, rb); done = true; break;
-      case 3 * 4 + ZV_REFERENCE:
-        switch (zu_cfg) {   // tile variants for the occupancy / halo-overhead sweep (MVTV_ZU_CFG); 0 = the measured default
-          case 1: launch_zu_march<T, ZuCfg<3, 32, 8, 1>, ZV_REFERENCE>(a, rb); break;    // 256 threads
-          case 2: launch_zu_march<T, ZuCfg<3, 64, 8, 1>, ZV_REFERENCE>(a, rb); break;    // 512 threads, less x halo
-          case 3: launch_zu_march<T, ZuCfg<3, 64, 4, 1>, ZV_REFERENCE>(a, rb); break;    // 256 threads
-          case 4: launch_zu_march<T, ZuCfg<3, 16, 16, 1>, ZV_REFERENCE>(a, rb); break;   // 256 threads
-          default: launch_zu_march<T, ZuCfg<3, 32, 16, 1>, ZV_REFERENCE>(a, rb); break;
-        }
-        done = true;
-        break;
-      case 3 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<3, 32, 16, 1>, ZV_INTENDED>(a, rb); done = true; break;
-      case 4 * 4 + ZV_REFERENCE:
-        switch (zu_cfg) {
-          case 1: launch_zu_march<T, ZuCfg<4, 16, 4, 4>, ZV_REFERENCE>(a, rb); break;    // 256 threads: no register spills
-          case 2: launch_zu_march<T, ZuCfg<4, 8, 8, 4>, ZV_REFERENCE>(a, rb); break;     // 256 threads
-          case 3: launch_zu_march<T, ZuCfg<4, 8, 8, 8>, ZV_REFERENCE>(a, rb); break;     // 512 threads, cubic tile
-          case 4: launch_zu_march<T, ZuCfg<4, 16, 8, 2>, ZV_REFERENCE>(a, rb); break;    // 256 threads
-          default: launch_zu_march<T, ZuCfg<4, 16, 8, 4>, ZV_REFERENCE>(a, rb); break;
-        }
-        done = true;
-        break;
-      case 4 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<4, 16, 8, 4>, ZV_INTENDED>(a, rb); done = true; break;
+      // tiles from the measured sweep (profiles/r2_call1_zu_probe.log): 3-D 16x16 (6.11 against 6.39 ms per launch on 512^3),
+      // 4-D 8x8x4 with 256 threads and no register spills (17.9 against 21.2 ms on 96^4)
+      case 3 * 4 + ZV_REFERENCE: launch_zu_march<T, ZuCfg<3, 16, 16, 1>, ZV_REFERENCE>(a, rb); done = true; break;
+      case 3 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<3, 16, 16, 1>, ZV_INTENDED>(a, rb); done = true; break;
+      case 4 * 4 + ZV_REFERENCE: launch_zu_march<T, ZuCfg<4, 8, 8, 4>, ZV_REFERENCE>(a, rb); done = true; break;
+      case 4 * 4 + ZV_INTENDED: launch_zu_march<T, ZuCfg<4, 8, 8, 4>, ZV_INTENDED>(a, rb); done = true; break;
       default: break;
     }
   }
@@ -839,20 +835,48 @@ template <> struct StepShape<2> { using Cfg = StepCfg<1, 256, 2,  1, 1, 1, 3>; }
 template <> struct StepShape<3> { using Cfg = StepCfg<2,  32, 1, 16, 4, 1, 4>; };   // 32x16 tile, 128 threads, 64 KB
 template <> struct StepShape<4> { using Cfg = StepCfg<3,  32, 1,  8, 2, 4, 3>; };   // 32x8x4 tile, 512 threads, 163 KB
 
+// Tile variants of the strip kernels, chosen from the measured sweeps (profiles/r1_final2_step2d_probe*.log, r2_call1_*.log):
+//   2-D (4096^2): direction + SpMV strips of 128 (4 vertices per lane) 111 us; first preconditioner pass 64 registers, 32 warps
+//       per SM, diag(c) derived from dinv 84 us; Horner passes 3 CTAs of 8 warps per SM; fused update 8 warps
+//   3-D (512^3): direction + SpMV 4 warps x 4 rows 1.02 ms; preconditioner passes 4 warps x 3 rows 0.78 ms
+using S2Step = Step2dCfg<4, 1, 4, 0>;
+using S2Prec = Step2dCfg<8, 1, 2, 4, true>;
+using S2Fuse = Fused2dCfg<8, 0>;
+constexpr int S2_HORNER_WARPS = 8, S2_HORNER_MINB = 3, S2_INIT_WARPS = 4;
+using S3Step = Step3dCfg<4, 4>;
+using S3Prec = Step3dCfg<4, 3>;
+// candidates of the two new modes (MVTV_TUNE=fuse3d=k / horner3d=k), to be fixed by the next measurement
+template <int K> struct S3FuseSel { using Cfg = Step3dCfg<4, 2>; };
+template <> struct S3FuseSel<1> { using Cfg = Step3dCfg<4, 3>; };
+template <> struct S3FuseSel<2> { using Cfg = Step3dCfg<8, 2>; };
+template <int K> struct S3HornerSel { using Cfg = Step3dCfg<4, 3>; };
+template <> struct S3HornerSel<1> { using Cfg = Step3dCfg<4, 4>; };
+template <> struct S3HornerSel<2> { using Cfg = Step3dCfg<4, 2>; };
+
 template <typename T, int P>
-int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, int prec, long long &inner, int &status) {
+int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, int deg, long long &inner, int &status) {
   using Cfg = typename StepShape<P>::Cfg;
   constexpr int Q = P - 1;
+  const int fam = cg_family;
+  // the family is a run-time property of the plan, the kernels are templates on P: guard the instantiations
+  constexpr bool HAS2D = (P == 2), HAS3D = (P == 3);
+  deg = std::max(0, std::min(deg, max_degree));
   if (!(dinv_rho == rhoM)) {
     k_make_dinv<T, P><<<dim3(grid.x, (unsigned)dt.nz + 2, 1), block, 0, stream>>>(dt, st, (const T *)cnt, rhoM, (T *)dinv);
     MVTV_CUDA(cudaGetLastError());
     dinv_rho = rhoM;
     launches += 1;
   }
+  const bool fused = fused_update && deg >= 1;   // update + first preconditioner pass in one kernel, r out of place
+  if (fused && !r2) {
+    MVTV_CUDA(cudaMalloc(&r2, (size_t)dt.usz * esz()));
+    MVTV_CUDA(cudaMemsetAsync(r2, 0, (size_t)dt.usz * esz(), stream));
+  }
   CgArgs<T> a;
   a.x = (T *)theta;
   a.xold = (T *)xold;
   a.r = (T *)r;
+  a.r2 = fused ? (T *)r2 : nullptr;
   a.q = (T *)q;
   a.pbuf[0] = (T *)pbuf[0];
   a.pbuf[1] = (T *)pbuf[1];
@@ -864,42 +888,135 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   a.S = S;
   a.raw = (world > 1 && !d_peer) ? raw : nullptr;
   a.peer = d_peer;
-  const bool fold = d_peer && fold_commit;   // opt-in: commits folded into the reducing kernels (no k_cg_peer_commit_* launches)
+  const bool fold = d_peer && fold_commit;   // commits folded into the reducing kernels (no k_cg_peer_commit_* launches)
   a.fold = fold ? 1 : 0;
   a.seq_red = 0;
   a.seq_halo = 0;
   a.seq_zhalo = 0;
   a.z = (T *)zbuf;
-  a.prec = prec;
-  {
-    // degree-1 polynomial in D^-1 M whose residual 1 - t P(t) is the Chebyshev polynomial T2 on [bmax/30, bmax]
-    const double b = cheb_bmax, lo = b / cheb1_kappa, th = 0.5 * (b + lo), de = 0.5 * (b - lo);
-    const double T2 = 2.0 * (th / de) * (th / de) - 1.0;
-    a.pc0 = 4.0 * th / (de * de * T2);
-    a.pc1 = -2.0 / (de * de * T2);
-  }
+  a.prec = deg;
+  // coefficients c_0 .. c_d of the degree-d polynomial P in D^-1 M whose residual 1 - t P(t) is the Chebyshev polynomial
+  // T_{d+1} on [bmax/kappa, bmax]; Horner form: w_1 = c_d A z0 + c_{d-1} z0, w_k = A w_{k-1} + c_{d-k} z0, z = w_d
+  double hc[8] = {0};
+  if (deg >= 1) cheb_poly_coeffs(deg, cheb_bmax, cheb_kappa, hc);
+  a.pc0 = deg >= 1 ? hc[deg - 1] : 0.0;
+  a.pc1 = deg >= 1 ? hc[deg] : 0.0;
   a.rho = rho;
   a.uscale = usc;
   a.rhoM = rhoM;
   a.rtol2 = rtol * rtol;
+  int nsm = 148;
+  MVTV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+  const int m0 = (int)dt.m[0], m1 = Q >= 2 ? (int)dt.m[1] : 1, m2 = Q >= 3 ? (int)dt.m[2] : 1;
+  // launch shape of a marching kernel: in-plane tiles x chunks of the last axis.  Chunks are sized per kernel (their register
+  // counts, hence resident CTAs per SM, differ) to fill whole waves of (SMs x resident CTAs) while keeping chunks >= 16 planes
+  // so the two extra planes a chunk stages stay cheap.
+  auto chunking = [&](unsigned tiles, int occ, int &zchunk_out) {
+    const long long slots = (long long)nsm * std::max(occ, 1);
+    int nchunk = 1;
+    double best = -1.0;
+    const int maxchunk = std::max(1, std::min(dt.nz / 16, 4096));
+    for (int nc = 1; nc <= maxchunk; ++nc) {
+      const int zc = (dt.nz + nc - 1) / nc;
+      const int ncr = (dt.nz + zc - 1) / zc;
+      const long long total = (long long)tiles * ncr;
+      if (total > (1ll << 16)) break;
+      const long long waves = (total + slots - 1) / slots;
+      const double eff = (double)total / (double)(waves * slots) * ((double)zc / (zc + 2.0));
+      if (eff > best + 1e-9) { best = eff; nchunk = ncr; }
+    }
+    zchunk_out = (dt.nz + nchunk - 1) / nchunk;
+    nchunk = (dt.nz + zchunk_out - 1) / zchunk_out;
+    return dim3(tiles, (unsigned)nchunk, 1);
+  };
+  auto sel3 = [](int k, auto &&fn) {   // run fn with the candidate index as a compile-time constant
+    switch (k) {
+      case 1: fn(std::integral_constant<int, 1>{}); break;
+      case 2: fn(std::integral_constant<int, 2>{}); break;
+      default: fn(std::integral_constant<int, 0>{}); break;
+    }
+  };
+  // occupancy queries are per device and per kernel: cache them per (device, family, slot)
+  struct Shapes { bool set = false; int occ[8] = {1, 1, 1, 1, 1, 1, 1, 1}; };
+  static Shapes shapes_dev[64][3][9];   // tile candidates have their own occupancies
+  Shapes &sh = shapes_dev[device & 63][fam][(tune_fuse3d % 3) * 3 + (tune_horner3d % 3)];
+  enum { K_STEP_J = 0, K_STEP_Z = 1, K_PREC = 2, K_HORNER = 3, K_FUSED = 4, K_INIT = 5 };
+  const size_t smem = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_JACOBI>();
+  const size_t smem2 = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_Z>();
+  if (!sh.set) {
+    auto occ_of = [&](auto kern, int nt, size_t sm) {
+      int o = 1;
+      MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, nt, sm));
+      return std::max(o, 1);
+    };
+    if (fam == CGF_RING) {
+      MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_JACOBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      sh.occ[K_STEP_J] = occ_of(k_cg_step<T, Cfg, STEP_JACOBI>, Cfg::NT, smem);
+      sh.occ[K_STEP_Z] = occ_of(k_cg_step<T, Cfg, STEP_Z>, Cfg::NT, smem2);
+      sh.occ[K_PREC] = occ_of(k_cg_step<T, Cfg, STEP_PREC>, Cfg::NT, smem2);
+    }
+    if constexpr (HAS2D) {
+      if (fam == CGF_STRIP2D) {
+        sh.occ[K_STEP_J] = occ_of(k_cg_step2d<T, S2Step, STEP_JACOBI>, S2Step::NT, 0);
+        sh.occ[K_STEP_Z] = occ_of(k_cg_step2d<T, S2Step, STEP_Z>, S2Step::NT, 0);
+        sh.occ[K_PREC] = occ_of(k_cg_step2d<T, S2Prec, STEP_PREC>, S2Prec::NT, 0);
+        sh.occ[K_HORNER] = occ_of(k_cg_horner2d<T, S2_HORNER_WARPS, S2_HORNER_MINB, false>, 32 * S2_HORNER_WARPS, 0);
+        sh.occ[K_FUSED] = occ_of(k_cg_updprec2d<T, S2Fuse>, S2Fuse::NT, 0);
+        sh.occ[K_INIT] = occ_of(k_cg_init2d<T, S2_INIT_WARPS>, 32 * S2_INIT_WARPS, 0);
+      }
+    }
+    if constexpr (HAS3D) {
+      if (fam == CGF_STRIP3D) {
+        sh.occ[K_STEP_J] = occ_of(k_cg_step3d<T, S3Step, STEP_JACOBI>, S3Step::NT, 0);
+        sh.occ[K_STEP_Z] = occ_of(k_cg_step3d<T, S3Step, STEP_Z>, S3Step::NT, 0);
+        sh.occ[K_PREC] = occ_of(k_cg_step3d<T, S3Prec, STEP_PREC>, S3Prec::NT, 0);
+        sel3(tune_horner3d, [&](auto k) { using C3 = typename S3HornerSel<decltype(k)::value>::Cfg; sh.occ[K_HORNER] = occ_of(k_cg_step3d<T, C3, STEP_HORNER>, C3::NT, 0); });
+        sel3(tune_fuse3d, [&](auto k) { using C3 = typename S3FuseSel<decltype(k)::value>::Cfg; sh.occ[K_FUSED] = occ_of(k_cg_step3d<T, C3, STEP_UPDPREC>, C3::NT, 0); });
+      }
+    }
+    sh.set = true;
+  }
+  unsigned tiles_step, tiles_prec, tiles_horner = 1, tiles_fused = 1;
+  if (fam == CGF_STRIP2D) {
+    tiles_step = (unsigned)((m0 + S2Step::TX - 1) / S2Step::TX);
+    tiles_prec = (unsigned)((m0 + S2Prec::TX - 1) / S2Prec::TX);
+    tiles_horner = (unsigned)((m0 + 64 * S2_HORNER_WARPS - 1) / (64 * S2_HORNER_WARPS));
+    tiles_fused = (unsigned)((m0 + S2Fuse::TX - 1) / S2Fuse::TX);
+  } else if (fam == CGF_STRIP3D) {
+    tiles_step = (unsigned)(((m0 + S3Step::TX - 1) / S3Step::TX) * ((m1 + S3Step::TY - 1) / S3Step::TY));
+    tiles_prec = (unsigned)(((m0 + S3Prec::TX - 1) / S3Prec::TX) * ((m1 + S3Prec::TY - 1) / S3Prec::TY));
+    sel3(tune_horner3d, [&](auto k) { using C3 = typename S3HornerSel<decltype(k)::value>::Cfg; tiles_horner = (unsigned)(((m0 + C3::TX - 1) / C3::TX) * ((m1 + C3::TY - 1) / C3::TY)); });
+    sel3(tune_fuse3d, [&](auto k) { using C3 = typename S3FuseSel<decltype(k)::value>::Cfg; tiles_fused = (unsigned)(((m0 + C3::TX - 1) / C3::TX) * ((m1 + C3::TY - 1) / C3::TY)); });
+  } else {
+    tiles_step = tiles_prec = (unsigned)(((m0 + Cfg::TX - 1) / Cfg::TX) * ((m1 + Cfg::TY - 1) / Cfg::TY) * ((m2 + Cfg::TW - 1) / Cfg::TW));
+  }
+  int zc_step = 1, zc_prec = 1, zc_horner = 1, zc_fused = 1;
+  const dim3 gs = chunking(tiles_step, sh.occ[deg ? K_STEP_Z : K_STEP_J], zc_step);
+  const dim3 gs_prec = chunking(tiles_prec, sh.occ[K_PREC], zc_prec);
+  const dim3 gs_horner = chunking(tiles_horner, sh.occ[K_HORNER], zc_horner);
+  const dim3 gs_fused = chunking(tiles_fused, sh.occ[K_FUSED], zc_fused);
+  const int gu = (int)std::max<long long>(1, std::min<long long>(148 * 8, (dt.Nloc + 1023) / 1024));
   const dim3 g = grid_owned();
+
+  // ---- r = b - M theta, theta_old = theta, r.z (Jacobi), r.r, b.b
   a.seq_red = ++red_seq;
   a.seq_halo = ++halo_seq;
   prof_begin(MVTV_KC_CG_INIT);
-  if (P == 2 && init2d) {   // opt-in: marching / shuffle form (cg_init2d.cuh)
-    constexpr int IW = 4;
-    int occ = 1, nsm_i = 148;
-    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_init2d<T, IW>, 32 * IW, 0));
-    MVTV_CUDA(cudaDeviceGetAttribute(&nsm_i, cudaDevAttrMultiProcessorCount, device));
-    const long long tiles_i = ((long long)dt.m[0] + 64 * IW - 1) / (64 * IW);
-    long long nchunk = ((long long)nsm_i * std::max(occ, 1) + tiles_i - 1) / tiles_i;
-    nchunk = std::max(1ll, std::min<long long>(nchunk, std::max(1, dt.nz / 8)));
-    const int zchunk_i = (int)((dt.nz + nchunk - 1) / nchunk);
-    nchunk = (dt.nz + zchunk_i - 1) / zchunk_i;
-    k_cg_init2d<T, IW><<<dim3((unsigned)tiles_i, (unsigned)nchunk, 1), 32 * IW, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1}, zchunk_i);
-  } else {
-    k_cg_init<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1});
+  bool init_done = false;
+  if constexpr (HAS2D) {
+    if (fam == CGF_STRIP2D) {   // marching / shuffle form (cg_init2d.cuh): 199 against 369 us on 4096^2
+      const long long tiles_i = ((long long)m0 + 64 * S2_INIT_WARPS - 1) / (64 * S2_INIT_WARPS);
+      long long nchunk = ((long long)nsm * sh.occ[K_INIT] + tiles_i - 1) / tiles_i;
+      nchunk = std::max(1ll, std::min<long long>(nchunk, std::max(1, dt.nz / 8)));
+      const int zchunk_i = (int)((dt.nz + nchunk - 1) / nchunk);
+      nchunk = (dt.nz + zchunk_i - 1) / zchunk_i;
+      k_cg_init2d<T, S2_INIT_WARPS><<<dim3((unsigned)tiles_i, (unsigned)nchunk, 1), 32 * S2_INIT_WARPS, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1}, zchunk_i);
+      init_done = true;
+    }
   }
+  if (!init_done) k_cg_init<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1});
   prof_end();
   MVTV_CUDA(cudaGetLastError());
   launches += 1;
@@ -912,199 +1029,136 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     k_cg_commit_init<<<1, 1, 0, stream>>>(S, raw);
     launches += 1;
   }
-  // fused direction + SpMV launch shape: in-plane tiles x chunks of the last axis.  Chunks are sized per kernel
-  // variant (their register counts, hence resident CTAs per SM, differ) to fill whole waves of (SMs x resident CTAs)
-  // while keeping chunks >= 16 planes so the two extra planes a chunk stages stay cheap.
-  const int m0 = (int)dt.m[0], m1 = Q >= 2 ? (int)dt.m[1] : 1, m2 = Q >= 3 ? (int)dt.m[2] : 1;
-  const unsigned tiles = (unsigned)(((m0 + Cfg::TX - 1) / Cfg::TX) * ((m1 + Cfg::TY - 1) / Cfg::TY) *
-                                    ((m2 + Cfg::TW - 1) / Cfg::TW));
-  const size_t smem = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_JACOBI>();
-  const size_t smem2 = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_Z>();
-  static bool attr_set_dev[64] = {false};
-  static int occ3_dev[64][3];
-  const int di = device & 63;
-  int *occ3 = occ3_dev[di];
-  if (!attr_set_dev[di]) {
-    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_JACOBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    MVTV_CUDA(cudaFuncSetAttribute(k_cg_step<T, Cfg, STEP_PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[STEP_JACOBI], k_cg_step<T, Cfg, STEP_JACOBI>, Cfg::NT, smem));
-    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[STEP_Z], k_cg_step<T, Cfg, STEP_Z>, Cfg::NT, smem2));
-    MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3[STEP_PREC], k_cg_step<T, Cfg, STEP_PREC>, Cfg::NT, smem2));
-    for (int k = 0; k < 3; ++k) if (occ3[k] < 1) occ3[k] = 1;
-    attr_set_dev[di] = true;
-  }
-  int nsm = 148;
-  MVTV_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
-  auto chunking = [&](int occ, int &zchunk_out) {
-    const long long slots = (long long)nsm * occ;
-    int nchunk = 1;
-    double best = -1.0;
-    const int maxchunk = std::max(1, std::min(dt.nz / 16, 256));
-    for (int nc = 1; nc <= maxchunk; ++nc) {
-      const int zc = (dt.nz + nc - 1) / nc;
-      const int ncr = (dt.nz + zc - 1) / zc;
-      const long long total = (long long)tiles * ncr;
-      const long long waves = (total + slots - 1) / slots;
-      const double eff = (double)total / (double)(waves * slots) * ((double)zc / (zc + 2.0));
-      if (eff > best + 1e-9) { best = eff; nchunk = ncr; }
+
+  // ---- the launches of one CG iteration
+  // first preconditioner pass, stand-alone (before the first iteration on the fused path, every iteration otherwise)
+  auto launch_prec_first = [&]() {
+    a.w_out_scr = (deg >= 2 && ((deg - 1) % 2 == 1)) ? 1 : 0;   // pass j writes z when deg - j is even
+    a.w_in_scr = 0;
+    a.final_pass = (deg == 1) ? 1 : 0;
+    a.pc0 = hc[deg - 1];
+    a.pc1 = hc[deg];
+    const RedBuf rbp{partials, counters + 5};
+    bool done = false;
+    if constexpr (HAS2D) {
+      if (fam == CGF_STRIP2D) {
+        if (deg == 1) k_cg_step2d<T, S2Prec, STEP_PREC><<<gs_prec, S2Prec::NT, 0, stream>>>(dt, st, a, rbp, zc_prec);
+        else k_cg_horner2d<T, S2_HORNER_WARPS, S2_HORNER_MINB, true><<<gs_horner, 32 * S2_HORNER_WARPS, 0, stream>>>(dt, st, a, rbp, zc_horner);
+        done = true;
+      }
     }
-    zchunk_out = (dt.nz + nchunk - 1) / nchunk;
-    nchunk = (dt.nz + zchunk_out - 1) / zchunk_out;
-    return dim3(tiles, (unsigned)nchunk, 1);
+    if constexpr (HAS3D) {
+      if (fam == CGF_STRIP3D) {
+        k_cg_step3d<T, S3Prec, STEP_PREC><<<gs_prec, S3Prec::NT, 0, stream>>>(dt, st, a, rbp, zc_prec);
+        done = true;
+      }
+    }
+    if (!done) k_cg_step<T, Cfg, STEP_PREC><<<gs_prec, Cfg::NT, smem2, stream>>>(dt, st, a, rbp, zc_prec);
+    launches += 1;
   };
-  int zchunk = 1, zchunk_prec = 1;
-  dim3 gs = chunking(occ3[prec ? STEP_Z : STEP_JACOBI], zchunk);
-  dim3 gs_prec = chunking(occ3[STEP_PREC], zchunk_prec);
-  // 2-D meshes with an even m0: the shuffle-based kernel (no shared memory), one 64-vertex strip per warp
-  const bool use2d = (P == 2) && step2d;
-  // tile variants: warps per CTA, rows in flight per lane, vertices per lane, resident CTAs asked of the compiler.
-  // The direction + SpMV kernel (5-6 N words) and the preconditioner kernel (3 N words) have different sweet spots.
-  auto dispatch2d = [&](auto &&fn) {          // STEP_JACOBI / STEP_Z (MVTV_STEP2D_CFG)
-    switch (step2d_cfg) {
-      case 1: fn(Step2dCfg<8, 1, 2, 4>{}); break;
-      case 2: fn(Step2dCfg<8, 1, 4, 2>{}); break;
-      case 3: fn(Step2dCfg<8, 1, 2, 3>{}); break;
-      case 4: fn(Step2dCfg<4, 2, 2, 0>{}); break;
-      default: fn(Step2dCfg<4, 1, 4, 0>{}); break;
+  // Horner passes 2 .. deg (strip kernels, one GPU)
+  auto launch_horner_rest = [&]() {
+    for (int j = 2; j <= deg; ++j) {
+      a.w_out_scr = ((deg - j) % 2 == 1) ? 1 : 0;
+      a.w_in_scr = ((deg - j + 1) % 2 == 1) ? 1 : 0;
+      a.final_pass = (j == deg) ? 1 : 0;
+      a.pc0 = hc[deg - j];
+      a.pc1 = 0.0;
+      const RedBuf rbp{partials, counters + 5};
+      if constexpr (HAS2D) {
+        if (fam == CGF_STRIP2D)
+          k_cg_horner2d<T, S2_HORNER_WARPS, S2_HORNER_MINB, false><<<gs_horner, 32 * S2_HORNER_WARPS, 0, stream>>>(dt, st, a, rbp, zc_horner);
+      }
+      if constexpr (HAS3D) {
+        if (fam == CGF_STRIP3D)
+          sel3(tune_horner3d, [&](auto k) {
+            using C3 = typename S3HornerSel<decltype(k)::value>::Cfg;
+            k_cg_step3d<T, C3, STEP_HORNER><<<gs_horner, C3::NT, 0, stream>>>(dt, st, a, rbp, zc_horner);
+          });
+      }
+      launches += 1;
     }
   };
-  auto dispatch2d_prec = [&](auto &&fn) {     // STEP_PREC (MVTV_STEP2D_PREC_CFG)
-    switch (step2d_prec_cfg) {
-      case 1: fn(Step2dCfg<8, 1, 2, 5, true>{}); break;
-      case 2: fn(Step2dCfg<8, 1, 2, 6, true>{}); break;
-      case 3: fn(Step2dCfg<16, 1, 2, 2, true>{}); break;
-      case 4: fn(Step2dCfg<4, 1, 2, 8, true>{}); break;
-      case 5: fn(Step2dCfg<8, 1, 2, 4, false>{}); break;   // reads diag(c) like k_cg_step (4 N words)
-      case 6: fn(Step2dCfg<8, 1, 2, 4, true, true>{}); break;
-      case 7: fn(Step2dCfg<8, 1, 2, 3, true, true>{}); break;
-      case 8: fn(Step2dCfg<8, 1, 2, 3, true, false>{}); break;
-      case 9: fn(Step2dCfg<8, 1, 2, 4, true, false, true>{}); break;    // 32-bit in-slab offsets
-      case 10: fn(Step2dCfg<8, 1, 2, 4, true, true, true>{}); break;
-      case 11: fn(Step2dCfg<8, 1, 2, 5, true, true, true>{}); break;    // <= 51 registers, 40 warps per SM
-      default: fn(Step2dCfg<8, 1, 2, 4, true>{}); break;
+  auto commit_rz = [&]() {   // world > 1 (degree 1): r.z across the ranks, then the ghost planes of z
+    if (fold) {
+    } else if (d_peer) {
+      k_cg_peer_commit_rz<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
+      launches += 1;
+    } else if (world > 1) {
+      allreduce(raw, 1, ncclSum);
+      k_cg_commit_rz<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
+      exchange_ghosts<T>((T *)zbuf);
+      launches += 1;
     }
   };
-  auto chunking2 = [&](unsigned tiles2, int occ, int &zchunk_out) {
-    const long long slots = (long long)nsm * std::max(occ, 1);
-    int nchunk = 1;
-    double best = -1.0;
-    const int maxchunk = std::max(1, std::min(dt.nz / 16, 4096));
-    for (int nc = 1; nc <= maxchunk; ++nc) {
-      const int zc = (dt.nz + nc - 1) / nc;
-      const int ncr = (dt.nz + zc - 1) / zc;
-      const long long total = (long long)tiles2 * ncr;
-      if (total > (1ll << 16)) break;
-      const long long waves = (total + slots - 1) / slots;
-      const double eff = (double)total / (double)(waves * slots) * ((double)zc / (zc + 2.0));
-      if (eff > best + 1e-9) { best = eff; nchunk = ncr; }
+  auto launch_step = [&]() {   // p = z + beta p (Jacobi: z = D^-1 r on the fly), q = M p, p.q
+    const RedBuf rbs{partials, counters + 2};
+    bool done = false;
+    if constexpr (HAS2D) {
+      if (fam == CGF_STRIP2D) {
+        if (deg) k_cg_step2d<T, S2Step, STEP_Z><<<gs, S2Step::NT, 0, stream>>>(dt, st, a, rbs, zc_step);
+        else k_cg_step2d<T, S2Step, STEP_JACOBI><<<gs, S2Step::NT, 0, stream>>>(dt, st, a, rbs, zc_step);
+        done = true;
+      }
     }
-    zchunk_out = (dt.nz + nchunk - 1) / nchunk;
-    nchunk = (dt.nz + zchunk_out - 1) / zchunk_out;
-    return dim3(tiles2, (unsigned)nchunk, 1);
-  };
-  if (use2d) {
-    dispatch2d([&](auto cfg) {
-      using C2 = decltype(cfg);
-      int occ = 1;
-      if (prec) MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step2d<T, C2, STEP_Z>, C2::NT, 0));
-      else MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step2d<T, C2, STEP_JACOBI>, C2::NT, 0));
-      gs = chunking2((unsigned)((m0 + C2::TX - 1) / C2::TX), occ, zchunk);
-    });
-    if (prec) dispatch2d_prec([&](auto cfg) {
-      using C2 = decltype(cfg);
-      int occ = 1;
-      MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step2d<T, C2, STEP_PREC>, C2::NT, 0));
-      gs_prec = chunking2((unsigned)((m0 + C2::TX - 1) / C2::TX), occ, zchunk_prec);
-    });
-  }
-  // 3-D meshes, opt-in: the shuffle-based kernel (cg_step3d.cuh); a warp owns 64 x RY vertices of a plane
-  const bool use3d = (P == 3) && step3d;
-  auto dispatch3d = [&](auto &&fn) {
-    switch (step3d_cfg) {
-      case 1: fn(Step3dCfg<4, 4>{}); break;
-      case 2: fn(Step3dCfg<8, 2>{}); break;
-      case 3: fn(Step3dCfg<4, 3>{}); break;
-      case 4: fn(Step3dCfg<8, 4>{}); break;
-      case 5: fn(Step3dCfg<4, 2, 0, false>{}); break;   // preconditioner reads diag(c)
-      case 6: fn(Step3dCfg<8, 1>{}); break;             // one row per warp: fewer registers, more warps, 3 rows loaded per row
-      case 7: fn(Step3dCfg<16, 1>{}); break;
-      default: fn(Step3dCfg<4, 2>{}); break;
+    if constexpr (HAS3D) {
+      if (fam == CGF_STRIP3D) {
+        if (deg) k_cg_step3d<T, S3Step, STEP_Z><<<gs, S3Step::NT, 0, stream>>>(dt, st, a, rbs, zc_step);
+        else k_cg_step3d<T, S3Step, STEP_JACOBI><<<gs, S3Step::NT, 0, stream>>>(dt, st, a, rbs, zc_step);
+        done = true;
+      }
+    }
+    if (!done) {
+      if (deg) k_cg_step<T, Cfg, STEP_Z><<<gs, Cfg::NT, smem2, stream>>>(dt, st, a, rbs, zc_step);
+      else k_cg_step<T, Cfg, STEP_JACOBI><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, rbs, zc_step);
+    }
+    launches += 1;
+    if (fold) {
+    } else if (d_peer) {
+      k_cg_peer_commit_pq<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
+      launches += 1;
+    } else if (world > 1) {
+      allreduce(raw, 1, ncclSum);
+      k_cg_commit_pq<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
+      launches += 1;
     }
   };
-  if (use3d) {
-    dispatch3d([&](auto cfg) {
-      using C3 = decltype(cfg);
-      const unsigned tiles3 = (unsigned)(((m0 + C3::TX - 1) / C3::TX) * ((m1 + C3::TY - 1) / C3::TY));
-      int occ = 1, occp = 1;
-      if (prec) MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step3d<T, C3, STEP_Z>, C3::NT, 0));
-      else MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step3d<T, C3, STEP_JACOBI>, C3::NT, 0));
-      MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, k_cg_step3d<T, C3, STEP_PREC>, C3::NT, 0));
-      gs = chunking2(tiles3, occ, zchunk);
-      gs_prec = chunking2(tiles3, occp, zchunk_prec);
-    });
-  }
-  const int gu = (int)std::max<long long>(1, std::min<long long>(148 * 8, (dt.Nloc + 1023) / 1024));
-  // 3-D meshes, opt-in: the hybrid kernel (cg_step3dh.cuh); a warp owns one row of 64 vertices, a CTA TY rows + 2 halo rows
-  const bool use3dh = (P == 3) && step3dh;
-  auto dispatch3dh = [&](auto &&fn) {
-    switch (step3d_cfg) {
-      case 1: fn(Step3dhCfg<6, 2>{}); break;
-      case 2: fn(Step3dhCfg<14, 1>{}); break;
-      case 3: fn(Step3dhCfg<14, 2>{}); break;
-      case 4: fn(Step3dhCfg<10, 1>{}); break;
-      case 5: fn(Step3dhCfg<6, 1, false>{}); break;   // preconditioner reads diag(c)
-      case 6: fn(Step3dhCfg<2, 2>{}); break;          // 128 threads per CTA
-      default: fn(Step3dhCfg<6, 1>{}); break;
+  auto launch_update = [&]() {   // theta += alpha p, r -= alpha q, r.r (Jacobi: r.z too); fused: + first preconditioner pass
+    const RedBuf rbu{partials, counters + 3};
+    if (fused) {
+      a.w_out_scr = (deg >= 2 && ((deg - 1) % 2 == 1)) ? 1 : 0;
+      a.w_in_scr = 0;
+      a.final_pass = (deg == 1) ? 1 : 0;
+      a.pc0 = hc[deg - 1];
+      a.pc1 = hc[deg];
+      if constexpr (HAS2D) {
+        if (fam == CGF_STRIP2D) k_cg_updprec2d<T, S2Fuse><<<gs_fused, S2Fuse::NT, 0, stream>>>(dt, st, a, rbu, zc_fused);
+      }
+      if constexpr (HAS3D) {
+        if (fam == CGF_STRIP3D)
+          sel3(tune_fuse3d, [&](auto k) {
+            using C3 = typename S3FuseSel<decltype(k)::value>::Cfg;
+            k_cg_step3d<T, C3, STEP_UPDPREC><<<gs_fused, C3::NT, 0, stream>>>(dt, st, a, rbu, zc_fused);
+          });
+      }
+      launches += 1;
+      return;
+    }
+    k_cg_update<T><<<gu, 256, 0, stream>>>(a, dt.plane, dt.Nloc, rbu);
+    launches += 1;
+    if (fold) {
+    } else if (d_peer) {
+      if (deg) k_cg_peer_commit_update_prec<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
+      else k_cg_peer_commit_update<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
+      launches += 1;
+    } else if (world > 1) {
+      allreduce(raw, 2, ncclSum);
+      if (deg) k_cg_commit_update_prec<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
+      else k_cg_commit_update<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
+      launches += 1;
     }
   };
-  if (use3dh) {
-    dispatch3dh([&](auto cfg) {
-      using CH = decltype(cfg);
-      const unsigned tiles3 = (unsigned)(((m0 + CH::TX - 1) / CH::TX) * ((m1 + CH::TY - 1) / CH::TY));
-      int occ = 1, occp = 1;
-      if (prec) MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step3dh<T, CH, STEP_Z>, CH::NT, 0));
-      else MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_step3dh<T, CH, STEP_JACOBI>, CH::NT, 0));
-      MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, k_cg_step3dh<T, CH, STEP_PREC>, CH::NT, 0));
-      gs = chunking2(tiles3, occ, zchunk);
-      gs_prec = chunking2(tiles3, occp, zchunk_prec);
-    });
-  }
-  // 2-D, one GPU, polynomial preconditioner, opt-in: vector update fused with the preconditioner (cg_fused2d.cuh)
-  const bool horner = use2d && prec && world == 1 && cheb_degree >= 2;   // opt-in: degree-d polynomial, one stencil pass per degree
-  double hc[8] = {0};
-  dim3 gs_horner = gs_prec;
-  int zchunk_horner = zchunk_prec;
-  if (horner) {
-    cheb_poly_coeffs(cheb_degree, cheb_bmax, cheb_kappa, hc);
-    int occ = 1;
-    if (horner_cfg == 1) MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_horner2d<T, 8, 3, false>, 256, 0));
-    else MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_horner2d<T, 8, 4, false>, 256, 0));
-    gs_horner = chunking2((unsigned)((m0 + 64 * 8 - 1) / (64 * 8)), occ, zchunk_horner);
-  }
-  const bool fused = use2d && prec && world == 1 && fuse_updprec && !horner;
-  dim3 gs_fused = gs_prec;
-  int zchunk_fused = zchunk_prec;
-  auto dispatch_fused = [&](auto &&fn) {
-    switch (fuse_cfg) {
-      case 1: fn(Fused2dCfg<8, 3>{}); break;   // <= 85 registers
-      case 2: fn(Fused2dCfg<4, 0>{}); break;
-      case 3: fn(Fused2dCfg<8, 4>{}); break;   // <= 64 registers
-      default: fn(Fused2dCfg<8, 0>{}); break;
-    }
-  };
-  if (fused) {
-    if (!r2) {
-      MVTV_CUDA(cudaMalloc(&r2, (size_t)dt.usz * esz()));
-      MVTV_CUDA(cudaMemsetAsync(r2, 0, (size_t)dt.usz * esz(), stream));
-    }
-    dispatch_fused([&](auto cfg) {
-      using CF = decltype(cfg);
-      int occ = 1;
-      MVTV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_updprec2d<T, CF>, CF::NT, 0));
-      gs_fused = chunking2((unsigned)((m0 + CF::TX - 1) / CF::TX), occ, zchunk_fused);
-    });
-  }
+
   bool first_prec_done = false;
   int launched = 0;
   int batch = std::max(2, std::min(last_cg_iters, 256));
@@ -1112,99 +1166,30 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   for (;;) {
     for (int k = 0; k < batch; ++k) {
       if (world > 1 && !d_peer) exchange_ghosts<T>((T *)r);
-      if (prec && !(fused && first_prec_done)) {  // z = P(D^-1 M) D^-1 r and r.z (fused path: only before the first iteration)
+      if (deg && !(fused && first_prec_done)) {  // z = P(D^-1 M) D^-1 r and r.z (fused path: only before the first iteration)
         first_prec_done = true;
         a.seq_red = ++red_seq;
         a.seq_zhalo = ++zhalo_seq;
         prof_begin(MVTV_KC_CG_PREC);
-        if (horner) {
-          const int d = cheb_degree;
-          for (int j = 1; j <= d; ++j) {   // pass j writes z when d - j is even, the (free) q buffer otherwise
-            T *w_out = ((d - j) % 2 == 0) ? (T *)zbuf : (T *)q;
-            const T *w_in = ((d - j) % 2 == 0) ? (const T *)q : (const T *)zbuf;
-            const RedBuf rbh{partials, counters + 5};
-            if (horner_cfg == 1) {
-              if (j == 1) k_cg_horner2d<T, 8, 3, true><<<gs_horner, 256, 0, stream>>>(dt, st, a, nullptr, w_out, hc[d - 1], hc[d], j == d, rbh, zchunk_horner);
-              else k_cg_horner2d<T, 8, 3, false><<<gs_horner, 256, 0, stream>>>(dt, st, a, w_in, w_out, hc[d - j], 0.0, j == d, rbh, zchunk_horner);
-            } else {
-              if (j == 1) k_cg_horner2d<T, 8, 4, true><<<gs_horner, 256, 0, stream>>>(dt, st, a, nullptr, w_out, hc[d - 1], hc[d], j == d, rbh, zchunk_horner);
-              else k_cg_horner2d<T, 8, 4, false><<<gs_horner, 256, 0, stream>>>(dt, st, a, w_in, w_out, hc[d - j], 0.0, j == d, rbh, zchunk_horner);
-            }
-          }
-          launches += d - 1;
-        } else if (use2d) dispatch2d_prec([&](auto cfg) {
-          using C2 = decltype(cfg);
-          k_cg_step2d<T, C2, STEP_PREC><<<gs_prec, C2::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
-        });
-        else if (use3d) dispatch3d([&](auto cfg) {
-          using C3 = decltype(cfg);
-          k_cg_step3d<T, C3, STEP_PREC><<<gs_prec, C3::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
-        });
-        else if (use3dh) dispatch3dh([&](auto cfg) {
-          using CH = decltype(cfg);
-          k_cg_step3dh<T, CH, STEP_PREC><<<gs_prec, CH::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
-        });
-        else k_cg_step<T, Cfg, STEP_PREC><<<gs_prec, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 5}, zchunk_prec);
+        launch_prec_first();
+        launch_horner_rest();
         prof_end();
-        if (fold) {
-        } else if (d_peer) {
-          k_cg_peer_commit_rz<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
-        } else if (world > 1) {
-          allreduce(raw, 1, ncclSum);
-          k_cg_commit_rz<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
-          exchange_ghosts<T>((T *)zbuf);
-        }
-        launches += (world > 1 && !fold) ? 2 : 1;
+        commit_rz();
       }
       a.seq_red = ++red_seq;       // a.seq_halo: the version the last producer of r posted
       prof_begin(MVTV_KC_CG_STEP);
-      if (use2d) {
-        dispatch2d([&](auto cfg) {
-          using C2 = decltype(cfg);
-          if (prec) k_cg_step2d<T, C2, STEP_Z><<<gs, C2::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
-          else k_cg_step2d<T, C2, STEP_JACOBI><<<gs, C2::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
-        });
-      } else if (use3d) {
-        dispatch3d([&](auto cfg) {
-          using C3 = decltype(cfg);
-          if (prec) k_cg_step3d<T, C3, STEP_Z><<<gs, C3::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
-          else k_cg_step3d<T, C3, STEP_JACOBI><<<gs, C3::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
-        });
-      } else if (use3dh) {
-        dispatch3dh([&](auto cfg) {
-          using CH = decltype(cfg);
-          if (prec) k_cg_step3dh<T, CH, STEP_Z><<<gs, CH::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
-          else k_cg_step3dh<T, CH, STEP_JACOBI><<<gs, CH::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
-        });
-      } else if (prec) k_cg_step<T, Cfg, STEP_Z><<<gs, Cfg::NT, smem2, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
-      else k_cg_step<T, Cfg, STEP_JACOBI><<<gs, Cfg::NT, smem, stream>>>(dt, st, a, RedBuf{partials, counters + 2}, zchunk);
+      launch_step();
       prof_end();
-      if (fold) {
-      } else if (d_peer) {
-        k_cg_peer_commit_pq<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
-      } else if (world > 1) {
-        allreduce(raw, 1, ncclSum);
-        k_cg_commit_pq<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
-      }
       a.seq_red = ++red_seq;
       a.seq_halo = ++halo_seq;
       prof_begin(MVTV_KC_CG_UPDATE);
-      if (fused) dispatch_fused([&](auto cfg) {
-        using CF = decltype(cfg);
-        k_cg_updprec2d<T, CF><<<gs_fused, CF::NT, 0, stream>>>(dt, st, a, (T *)r, (T *)r2, RedBuf{partials, counters + 3}, zchunk_fused);
-      });
-      else k_cg_update<T><<<gu, 256, 0, stream>>>(a, dt.plane, dt.Nloc, RedBuf{partials, counters + 3});
+      launch_update();
       prof_end();
-      if (fold) {
-      } else if (d_peer) {
-        if (prec) k_cg_peer_commit_update_prec<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
-        else k_cg_peer_commit_update<<<1, 1, 0, stream>>>(S, d_peer, a.seq_red, a.rtol2);
-      } else if (world > 1) {
-        allreduce(raw, 2, ncclSum);
-        if (prec) k_cg_commit_update_prec<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
-        else k_cg_commit_update<<<1, 1, 0, stream>>>(S, raw, a.rtol2);
+      if (fused && deg >= 2) {
+        prof_begin(MVTV_KC_CG_PREC);
+        launch_horner_rest();
+        prof_end();
       }
-      launches += (world > 1 && !fold) ? 4 : 2;
     }
     MVTV_CUDA(cudaGetLastError());
     launched += batch;
@@ -1334,10 +1319,14 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
   const double tol = (prm.tol > 0.0) ? prm.tol : (mode == MVTV_MODE_RCPP ? 1e-4 : 1e-3);
   const int max_counter = prm.max_counter > 0 ? prm.max_counter
                           : (mode == MVTV_MODE_CPP ? 2000 : (mode == MVTV_MODE_RCPP ? 3000 : 5000));
-  const double cg_rtol = prm.cg_rtol > 0.0 ? prm.cg_rtol : (dtype == MVTV_F64 ? 1e-13 : 1e-5);
+  // delta-scaled blocks (the mbs() driver's operators, cpp-code/utils.cpp:258-267) make the system badly conditioned at
+  // empty vertices: 1e-13 leaves ~2e-8 in theta there, 1e-14 keeps the 1e-9 parity bar
+  bool scaled = false;
+  for (int b = 0; b < bt.K; ++b) scaled = scaled || (bt.scale[b] != 1.0);
+  const double cg_rtol = prm.cg_rtol > 0.0 ? prm.cg_rtol : (dtype == MVTV_F64 ? (scaled ? 1e-14 : 1e-13) : 1e-5);
   const int cg_maxit = prm.cg_maxit > 0 ? prm.cg_maxit : (dtype == MVTV_F64 ? 20000 : 1000);
-  if (prm.precond != MVTV_PRECOND_JACOBI && prm.precond != MVTV_PRECOND_CHEB1 && prm.precond != MVTV_PRECOND_AUTO)
-    throw Error(MVTV_ERR_UNSUPPORTED, "precond must be MVTV_PRECOND_JACOBI, _CHEB1 or _AUTO");
+  if (prm.precond < MVTV_PRECOND_JACOBI || prm.precond > MVTV_PRECOND_CHEB4)
+    throw Error(MVTV_ERR_UNSUPPORTED, "precond must be one of MVTV_PRECOND_JACOBI, _CHEB1 .. _CHEB4, _AUTO");
   const long long launches0 = launches;
   const long long nvec = dt.usz;
   T *th = (T *)theta;
@@ -1407,10 +1396,19 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
     if (prm.max_passes > 0 && passes >= prm.max_passes) break;
     // b = Oty + rho*Dt*(alpha+u) ; theta = spsolve(sp_crosses, b)     cpp :115-116 / rcpp :112-113
     int cgst = MVTV_OK;
-    // AUTO: the polynomial pays off once plain Jacobi-PCG needs more than ~24 iterations (it halves the iteration
-    // count for one more stencil each); the estimate comes from the previous x-update on this plan
-    const double jac_equiv = last_cg_prec ? 1.9 * last_cg_iters : (double)last_cg_iters;
-    const int prec = (prm.precond == MVTV_PRECOND_CHEB1) ? 1 : (prm.precond == MVTV_PRECOND_AUTO ? (jac_equiv > 24.0) : 0);
+    // AUTO: the polynomial pays off once plain Jacobi-PCG needs more than ~24 iterations (degree d needs ~0.86 (d+1) times
+    // fewer iterations for d more stencil passes); the estimate comes from the previous x-update on this plan
+    const double jac_equiv = last_cg_prec ? 0.86 * (last_cg_prec + 1) * last_cg_iters : (double)last_cg_iters;
+    int prec;
+    switch (prm.precond) {
+      case MVTV_PRECOND_JACOBI: prec = 0; break;
+      case MVTV_PRECOND_CHEB1: prec = 1; break;
+      case MVTV_PRECOND_CHEB2: prec = 2; break;
+      case MVTV_PRECOND_CHEB3: prec = 3; break;
+      case MVTV_PRECOND_CHEB4: prec = 4; break;
+      default: prec = (jac_equiv > 24.0) ? auto_degree : 0; break;
+    }
+    prec = std::min(prec, max_degree);
     last_cg_prec = prec;
     switch (dt.P) {
       case 2: cg_solve<T, 2>(rho, uscale, rhoM, cg_rtol, cg_maxit, prec, inner, cgst); break;
@@ -1609,17 +1607,16 @@ int mvtv_plan_info(const mvtv_plan *plan, int64_t *N, int64_t *R, int64_t *z0, i
 int mvtv_plan_describe(const mvtv_plan *plan, char *buf, int64_t cap) {
   return guarded([&] {
     MVTV_REQUIRE(plan && buf && cap > 0, "null argument");
-    const bool s2 = plan->step2d && plan->dt.P == 2;
-    const bool s3 = (plan->step3d || plan->step3dh) && plan->dt.P == 3;
-    char tmp[512];
+    const char *fam = plan->cg_family == CGF_STRIP2D ? "k_cg_step2d" : (plan->cg_family == CGF_STRIP3D ? "k_cg_step3d" : "k_cg_step");
+    char tmp[640];
     snprintf(tmp, sizeof(tmp),
              "{\"p\": %d, \"dtype\": %d, \"world\": %d, \"zu\": \"%s\", \"cg_step\": \"%s\", \"cg_prec\": \"%s\", "
-             "\"cg_prec_words\": %d, \"collectives\": \"%s\", \"fold_commit\": %d}",
-             plan->p, plan->dtype, plan->world, plan->zu_variant >= 0 ? "k_zu_march" : "k_zu",
-             s2 ? "k_cg_step2d" : (s3 ? (plan->step3dh ? "k_cg_step3dh" : "k_cg_step3d") : "k_cg_step"),
-             s2 ? "k_cg_step2d" : (s3 ? (plan->step3dh ? "k_cg_step3dh" : "k_cg_step3d") : "k_cg_step"),
-             (s2 || (s3 && plan->step3d_cfg != 5)) ? 3 : 4,
-             plan->world == 1 ? "none" : (plan->d_peer ? "peer" : "nccl"), (plan->d_peer && plan->fold_commit) ? 1 : 0);
+             "\"cg_prec_words\": %d, \"fused_update\": %d, \"max_degree\": %d, \"auto_degree\": %d, \"last_degree\": %d, "
+             "\"collectives\": \"%s\", \"fold_commit\": %d}",
+             plan->p, plan->dtype, plan->world, plan->zu_variant >= 0 ? "k_zu_march" : "k_zu", fam, fam,
+             plan->cg_family == CGF_RING ? 4 : 3, plan->fused_update ? 1 : 0, plan->max_degree, plan->auto_degree,
+             plan->last_cg_prec, plan->world == 1 ? "none" : (plan->d_peer ? "peer" : "nccl"),
+             (plan->d_peer && plan->fold_commit) ? 1 : 0);
     MVTV_REQUIRE((int64_t)strlen(tmp) < cap, "buffer too small");
     strcpy(buf, tmp);
     return MVTV_OK;
@@ -1646,7 +1643,7 @@ int mvtv_plan_get_profile(mvtv_plan *plan, double *ms, int64_t *count) {
 int mvtv_plan_set_points_dev(mvtv_plan *plan, int64_t n, const double *data_dev, const double *y_dev,
                              const double *axes_dev) {
   return guarded([&] {
-    MVTV_REQUIRE(plan && data_dev && y_dev && axes_dev, "null argument");
+    MVTV_REQUIRE(plan && axes_dev && (n == 0 || (data_dev && y_dev)), "null argument");
     if (plan->dtype == MVTV_F64) plan->set_points_t<double>(n, data_dev, 1, n, y_dev, axes_dev);
     else plan->set_points_t<float>(n, data_dev, 1, n, y_dev, axes_dev);
     return MVTV_OK;
@@ -1660,8 +1657,8 @@ int mvtv_plan_set_points(mvtv_plan *plan, int64_t n, const double *data, const d
 int mvtv_plan_set_points_strided(mvtv_plan *plan, int64_t n, const double *data, int64_t ld_point, int64_t ld_axis,
                                  const double *y, const double *axes) {
   return guarded([&] {
-    MVTV_REQUIRE(plan && data && y && axes, "null argument");
-    MVTV_REQUIRE(n >= 1, "n must be >= 1");
+    MVTV_REQUIRE(plan && axes && (n == 0 || (data && y)), "null argument");
+    MVTV_REQUIRE(n >= (plan->world > 1 ? 0 : 1), "n must be >= 1 (world > 1: a rank may hold no points)");
     MVTV_REQUIRE((ld_point == 1 && ld_axis == n) || (ld_point == plan->p && ld_axis == 1),
                  "data must be dense column-major (1, n) or row-major (p, 1)");
     plan->use_device();
@@ -1672,8 +1669,10 @@ int mvtv_plan_set_points_strided(mvtv_plan *plan, int64_t n, const double *data,
     const auto t0 = std::chrono::steady_clock::now();
     double *buf = (double *)mvtv_plan::grow(plan->in_buf, plan->in_bytes, sizeof(double) * total);
     const auto t1 = std::chrono::steady_clock::now();
-    MVTV_CUDA(cudaMemcpyAsync(buf, data, sizeof(double) * nd, cudaMemcpyHostToDevice, plan->stream));
-    MVTV_CUDA(cudaMemcpyAsync(buf + nd, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, plan->stream));
+    if (n > 0) {
+      MVTV_CUDA(cudaMemcpyAsync(buf, data, sizeof(double) * nd, cudaMemcpyHostToDevice, plan->stream));
+      MVTV_CUDA(cudaMemcpyAsync(buf + nd, y, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, plan->stream));
+    }
     MVTV_CUDA(cudaMemcpyAsync(buf + nd + n, axes, sizeof(double) * (size_t)na, cudaMemcpyHostToDevice, plan->stream));
     if (trace) MVTV_CUDA(cudaStreamSynchronize(plan->stream));
     const auto t2 = std::chrono::steady_clock::now();
@@ -1803,7 +1802,8 @@ int mvtv_solve_path(mvtv_plan *plan, const mvtv_solve_params *prm, int32_t n_lam
         mses_out[i] = m;
         if (counters_out) counters_out[i] = r.counter;
         if (rhos_out) rhos_out[i] = r.rho;
-        if (m < best_mse) {  // first instance of the lowest MSE (cpp solvers.cpp:172-175)
+        if (i == 0 || m < best_mse) {  // first instance of the lowest MSE (cpp solvers.cpp:172-175); lambda 0 is
+                                       // always captured, so an all-NaN path still returns a model
           best_mse = m;
           best = i;
           if (theta_best_out || fitted_best_out) {

@@ -16,7 +16,8 @@ import weakref
 import numpy as np
 
 from . import _lib
-from ._lib import (F32, F64, MODE_CPP, MODE_PY, MODE_RCPP, PRECOND_AUTO, PRECOND_CHEB1, PRECOND_JACOBI, VARIANT_INTENDED,  # noqa: F401
+from ._lib import (F32, F64, MODE_CPP, MODE_PY, MODE_RCPP, PRECOND_AUTO, PRECOND_CHEB1, PRECOND_CHEB2, PRECOND_CHEB3, PRECOND_CHEB4,  # noqa: F401
+                   PRECOND_JACOBI, VARIANT_INTENDED,
                    VARIANT_REFERENCE, WARM_THETA_FROM_PLAN, WARM_U_FROM_PLAN, MvtvError, NotConverged)
 
 _MODES = {"cpp": MODE_CPP, "rcpp": MODE_RCPP, "py": MODE_PY, MODE_CPP: MODE_CPP, MODE_RCPP: MODE_RCPP,

@@ -17,7 +17,6 @@
 #include "../../multivartv_b200/csrc/zu_march.cuh"
 #include "../../multivartv_b200/csrc/cg_step2d.cuh"
 #include "../../multivartv_b200/csrc/cg_step3d.cuh"
-#include "../../multivartv_b200/csrc/cg_step3dh.cuh"
 #include "../../multivartv_b200/csrc/cg_fused2d.cuh"
 #include "../../multivartv_b200/csrc/cg_init2d.cuh"
 // clang-format on
@@ -276,20 +275,6 @@ static void check_3d(std::vector<long long> m, const std::vector<double> &deltas
     one(Step3dCfg<4, 4>{}, "k_cg_step3d<4,4>");
     one(Step3dCfg<8, 1>{}, "k_cg_step3d<8,1>");
     one(Step3dCfg<4, 2, 0, false>{}, "k_cg_step3d<4,2,c>");
-    auto hyb = [&](auto cfg, const char *name) {
-      using CH = decltype(cfg);
-      run_kernel(pb, MODE, [&](const CgArgs<double> &a, RedBuf rb) {
-        const unsigned tiles = (unsigned)(((dt.m[0] + CH::TX - 1) / CH::TX) * ((dt.m[1] + CH::TY - 1) / CH::TY));
-        cuda_emu::launch(dim3(tiles, nch, 1), dim3(CH::NT, 1, 1), 0, [&] { k_cg_step3dh<double, CH, MODE>(dt, st, a, rb, zchunk); });
-      }, shfl);
-      compare(name, pb, MODE, shfl, ref, 1e-12);
-      compare(name, pb, MODE, shfl, smem, 1e-12);
-    };
-    hyb(Step3dhCfg<6, 1>{}, "k_cg_step3dh<6,1>");
-    hyb(Step3dhCfg<6, 2>{}, "k_cg_step3dh<6,2>");
-    hyb(Step3dhCfg<14, 1>{}, "k_cg_step3dh<14,1>");
-    hyb(Step3dhCfg<2, 2>{}, "k_cg_step3dh<2,2>");
-    hyb(Step3dhCfg<6, 1, false>{}, "k_cg_step3dh<6,1,c>");
   }
 }
 
@@ -412,13 +397,6 @@ static void check_slabs_all(unsigned seed) {
       cuda_emu::launch(dim3(tiles, (unsigned)((dt.nz + zchunk - 1) / zchunk), 1), dim3(C3::NT, 1, 1), 0,
                        [&] { k_cg_step3d<double, C3, MODE>(dt, st, a, rb, zchunk); });
     });
-    check_slabs<MODE>("k_cg_step3dh<6,2>", {12, 10, 9}, d3, seed, world, [](const DimTab &dt, const StencilTab &st, const CgArgs<double> &a, RedBuf rb) {
-      using CH = Step3dhCfg<6, 2>;
-      const unsigned tiles = (unsigned)(((dt.m[0] + CH::TX - 1) / CH::TX) * ((dt.m[1] + CH::TY - 1) / CH::TY));
-      const int zchunk = (dt.nz + 1) / 2;
-      cuda_emu::launch(dim3(tiles, (unsigned)((dt.nz + zchunk - 1) / zchunk), 1), dim3(CH::NT, 1, 1), 0,
-                       [&] { k_cg_step3dh<double, CH, MODE>(dt, st, a, rb, zchunk); });
-    });
     check_slabs<MODE>("k_cg_step3d<8,1>", {70, 7, 8}, none, seed + 1, world, [](const DimTab &dt, const StencilTab &st, const CgArgs<double> &a, RedBuf rb) {
       using C3 = Step3dCfg<8, 1>;
       const unsigned tiles = (unsigned)(((dt.m[0] + C3::TX - 1) / C3::TX) * ((dt.m[1] + C3::TY - 1) / C3::TY));
@@ -478,7 +456,7 @@ static void check_fused(const char *name, std::vector<long long> m, const std::v
     const int zchunk = (dt.nz + nchunk - 1) / nchunk;
     const unsigned tiles = (unsigned)((dt.m[0] + CF::TX - 1) / CF::TX);
     cuda_emu::launch(dim3(tiles, (unsigned)((dt.nz + zchunk - 1) / zchunk), 1), dim3(CF::NT, 1, 1), 0,
-                     [&] { k_cg_updprec2d<double, CF>(dt, st, a, r0s.data(), r1s.data(), RedBuf{partials.data(), &counter}, zchunk); });
+                     [&] { a.r = r0s.data(); a.r2 = r1s.data(); k_cg_updprec2d<double, CF>(dt, st, a, RedBuf{partials.data(), &counter}, zchunk); });
     const std::vector<double> &rn = cur ? r0s : r1s;
     double ex = 0, er = 0, ez = 0;
     for (long long i = dt.plane; i < dt.plane + dt.Nloc; ++i) {

@@ -22,8 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-ENVKEYS = ["MVTV_INIT2D", "MVTV_FUSE_UPDPREC", "MVTV_FUSE_CFG", "MVTV_CHEB_DEGREE", "MVTV_CHEB_KAPPA", "MVTV_HORNER_CFG", "MVTV_STEP3D",
-           "MVTV_STEP3D_CFG", "MVTV_ZU_CFG", "MVTV_STEP2D", "MVTV_STEP2D_CFG", "MVTV_STEP2D_PREC_CFG", "MVTV_ZU", "EMU_NSM", "EMU_OCC"]
+ENVKEYS = ["MVTV_STEP", "MVTV_ZU_KERNEL", "EMU_NSM", "EMU_OCC"]
 
 
 def build_emulated_library(scratch):
@@ -77,14 +76,15 @@ def main():
     from oracle import c_oracle as co
     from tests.helpers import synth
 
-    def run(m, x, y, axes, env, passes, variant=0, lam=0.8, dtype=mv.F64):
+    def run(m, x, y, axes, env, passes, variant=0, lam=0.8, dtype=mv.F64, precond=mv.PRECOND_CHEB1):
         for k in ENVKEYS:
             os.environ.pop(k, None)
         os.environ.update(env)
         with mv.Plan(m, variant=variant, dtype=dtype) as pl:
             d = pl.describe()
             pl.set_points(x, y, axes)
-            out = pl.solve(lam, mode="rcpp", max_passes=passes, precond=mv.PRECOND_CHEB1, raise_on_nonconvergence=False, want_u=True)
+            out = pl.solve(lam, mode="rcpp", max_passes=passes, precond=precond, raise_on_nonconvergence=False, want_u=True)
+            d = pl.describe()
         for k in ENVKEYS:
             os.environ.pop(k, None)
         return out, d
@@ -130,50 +130,49 @@ def main():
             ok = ok and int(path["counters"][i]) == r["counter"] and np.abs(path["thetas"][i] - theta).max() <= 1e-9
         report(ok, "solve_path (cpp, 3 warm-started lambdas) vs oracle: counters %s" % list(path["counters"]))
 
-    # ---- 3. every opt-in kernel path (environment variables read at plan creation) against the default path
-    def sweep(m, n, seed, passes, envs, variant=0):
+    # ---- 3. every kernel family / preconditioner degree the host code can select, against the oracle and against each other:
+    # the strip kernels (default on even m0) with the fused update, Jacobi and Horner degrees 1..4, the shared-memory ring
+    # (MVTV_STEP=ring), the gather z/u kernel, and other SM counts / occupancies (the chunking of the marching kernels)
+    P = {"jacobi": mv.PRECOND_JACOBI, "cheb1": mv.PRECOND_CHEB1, "cheb2": mv.PRECOND_CHEB2, "cheb3": mv.PRECOND_CHEB3,
+         "cheb4": mv.PRECOND_CHEB4, "auto": mv.PRECOND_AUTO}
+
+    def sweep(m, n, seed, passes, cases, variant=0):
         p = len(m)
         x, y = synth(seed, n, p, 0.0, 1.0, 0.5)
         axes = [np.linspace(0, 1, d) for d in m]
-        ref, d0 = run(m, x, y, axes, {}, passes, variant)
         orc = co.mbs_one(x, y, m, axes, 0.8, mode=co.MODE_RCPP, max_passes=passes, variant=variant)
-        report(np.abs(ref["theta"] - orc["theta"]).max() <= 1e-9, "mesh %s default path (%s) vs oracle after %d passes: max|dtheta| %.2e, %d CG iterations" % (
-            m, d0["cg_step"], passes, np.abs(ref["theta"] - orc["theta"]).max(), ref["inner_iters"]))
-        for env, want_step, kind in envs:
-            out, d = run(m, x, y, axes, env, passes, variant)
-            et, eu = float(np.abs(out["theta"] - ref["theta"]).max()), float(np.abs(out["u"] - ref["u"]).max())
-            if kind == "same":       # same arithmetic up to summation order: same iteration count
-                ok = et <= 1e-12 and eu <= 1e-12 and out["inner_iters"] == ref["inner_iters"]
-            elif kind == "fused":    # one launch less per CG iteration
-                ok = et <= 1e-12 and eu <= 1e-12 and out["inner_iters"] == ref["inner_iters"] and out["kernel_launches"] < ref["kernel_launches"] - ref["inner_iters"] // 2
-            else:                    # another preconditioner: same solution to the CG tolerance, fewer iterations
-                ok = et <= 1e-9 and eu <= 1e-9 and out["inner_iters"] < ref["inner_iters"]
-            ok = ok and d["cg_step"] == want_step
-            report(ok, "  %-75s %-13s max|dtheta| %.1e max|du| %.1e CG %d (default %d) launches %d (%d)" % (
-                env, d["cg_step"], et, eu, out["inner_iters"], ref["inner_iters"], out["kernel_launches"], ref["kernel_launches"]))
+        base = {}
+        for env, prec, want_step, want_deg in cases:
+            out, d = run(m, x, y, axes, env, passes, variant, precond=P[prec])
+            et = float(np.abs(out["theta"] - orc["theta"]).max())
+            eu = float(np.abs(out["u"] - orc["u"]).max()) if orc.get("u") is not None else 0.0
+            ok = et <= 1e-9 and eu <= 1e-8 and out["passes"] == orc["passes"] and d["cg_step"] == want_step and d["last_degree"] == want_deg
+            key = (prec,)
+            if key in base:      # same preconditioner through another kernel family / launch shape: same iteration count
+                ok = ok and out["inner_iters"] == base[key]
+            else:
+                base[key] = out["inner_iters"]
+            report(ok, "  mesh %s %-22s %-7s %-12s degree %d: max|dtheta| %.1e max|du| %.1e CG %d launches %d" % (
+                m, env, prec, d["cg_step"], d["last_degree"], et, eu, out["inner_iters"], out["kernel_launches"]))
+        its = [base[(k,)] for k in ("jacobi", "cheb1", "cheb2", "cheb3", "cheb4") if (k,) in base]
+        report(all(a > b for a, b in zip(its[:2], its[1:2])), "  mesh %s: CG iterations by degree %s" % (m, its))
 
-    s2 = "k_cg_step2d"
-    envs2 = [({"MVTV_STEP2D": "smem"}, "k_cg_step", "same"), ({"MVTV_INIT2D": "1"}, s2, "same"), ({"MVTV_FUSE_UPDPREC": "1"}, s2, "fused"),
-             ({"MVTV_FUSE_UPDPREC": "1", "MVTV_FUSE_CFG": "2", "MVTV_INIT2D": "1"}, s2, "fused"),
-             ({"MVTV_CHEB_DEGREE": "2"}, s2, "prec"), ({"MVTV_CHEB_DEGREE": "3", "MVTV_HORNER_CFG": "1"}, s2, "prec"),
-             ({"MVTV_CHEB_DEGREE": "4", "MVTV_CHEB_KAPPA": "100"}, s2, "prec"),
-             ({"MVTV_STEP2D_PREC_CFG": "9"}, s2, "same"), ({"MVTV_STEP2D_PREC_CFG": "10"}, s2, "same"), ({"MVTV_STEP2D_PREC_CFG": "11"}, s2, "same"),
-             ({"EMU_NSM": "1", "EMU_OCC": "1"}, s2, "same"), ({"EMU_NSM": "16", "EMU_OCC": "4"}, s2, "same")]
-    sweep([66, 40], 2500, 1, 3, envs2[:7] if quick else envs2)
+    s2, s3, ring = "k_cg_step2d", "k_cg_step3d", "k_cg_step"
+    R = {"MVTV_STEP": "ring"}
+    cases2 = [({}, "jacobi", s2, 0), ({}, "cheb1", s2, 1), ({}, "cheb2", s2, 2), ({}, "cheb3", s2, 3), ({}, "cheb4", s2, 4),
+              (R, "jacobi", ring, 0), (R, "cheb1", ring, 1), (R, "cheb3", ring, 1),
+              ({"EMU_NSM": "1", "EMU_OCC": "1"}, "cheb3", s2, 3), ({"EMU_NSM": "16", "EMU_OCC": "4"}, "cheb2", s2, 2),
+              ({"MVTV_ZU_KERNEL": "gather"}, "cheb1", s2, 1)]
+    sweep([66, 40], 2500, 1, 3, cases2[:7] if quick else cases2)
     if not quick:
-        sweep([130, 33], 3000, 7, 2, [envs2[2], envs2[4], envs2[7]])
-    s3, sh = "k_cg_step3d", "k_cg_step3dh"
-    envs3 = [({"MVTV_STEP3D": "shfl"}, s3, "same"), ({"MVTV_STEP3D": "hyb"}, sh, "same"),
-             ({"MVTV_STEP3D": "shfl", "MVTV_STEP3D_CFG": "1", "MVTV_ZU_CFG": "1"}, s3, "same"),
-             ({"MVTV_STEP3D": "hyb", "MVTV_STEP3D_CFG": "1", "MVTV_ZU_CFG": "3"}, sh, "same"),
-             ({"MVTV_STEP3D": "shfl", "MVTV_STEP3D_CFG": "6", "MVTV_ZU_CFG": "2"}, s3, "same"),
-             ({"MVTV_STEP3D": "shfl", "MVTV_STEP3D_CFG": "5", "MVTV_ZU_CFG": "4"}, s3, "same"),
-             ({"MVTV_STEP3D": "hyb", "MVTV_STEP3D_CFG": "5"}, sh, "same"), ({"MVTV_STEP3D": "hyb", "MVTV_STEP3D_CFG": "6", "EMU_NSM": "16"}, sh, "same")]
-    sweep([16, 6, 34], 3000, 2, 2, envs3[:2] if quick else envs3, variant=1)   # non-cubic: the intended operator variant
+        sweep([130, 33], 3000, 7, 2, [cases2[1], cases2[3], cases2[6]])
+    cases3 = [({}, "jacobi", s3, 0), ({}, "cheb1", s3, 1), ({}, "cheb2", s3, 2), ({}, "cheb3", s3, 3), ({}, "cheb4", s3, 4),
+              (R, "jacobi", ring, 0), (R, "cheb1", ring, 1), ({"EMU_NSM": "16"}, "cheb3", s3, 3), ({"EMU_NSM": "2", "EMU_OCC": "1"}, "cheb2", s3, 2)]
+    sweep([16, 6, 34], 3000, 2, 2, cases3[:5] if quick else cases3, variant=1)   # non-cubic: the intended operator variant
     if not quick:
-        sweep([12, 12, 12], 1500, 3, 2, [({"MVTV_STEP3D": "shfl", "MVTV_STEP3D_CFG": str(c)}, s3, "same") for c in (2, 3, 4, 7)] +
-              [({"MVTV_STEP3D": "hyb", "MVTV_STEP3D_CFG": str(c)}, sh, "same") for c in (2, 3, 4)])
-        sweep([6, 6, 6, 6], 1500, 4, 2, [({"MVTV_ZU_CFG": str(c)}, "k_cg_step", "same") for c in (1, 2, 3, 4)])
+        sweep([12, 12, 12], 1500, 3, 2, [cases3[1], cases3[3], cases3[6], cases3[7]])
+        sweep([66, 5, 7], 1500, 5, 2, [cases3[0], cases3[1], cases3[2], cases3[3]], variant=1)
+        sweep([6, 6, 6, 6], 1500, 4, 2, [({}, "jacobi", ring, 0), ({}, "cheb1", ring, 1), ({}, "cheb4", ring, 1), ({"MVTV_ZU_KERNEL": "gather"}, "cheb1", ring, 1)])
     print("emu_lib: %d failure(s)" % FAIL)
     return 1 if FAIL else 0
 

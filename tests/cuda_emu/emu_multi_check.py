@@ -42,7 +42,7 @@ def main():
     _lib.load()
 
     J, C1 = mv.PRECOND_JACOBI, mv.PRECOND_CHEB1
-    cases = [  # dims, n, mode, lambda, max_passes, preconditioner, world, comm ("fold": peer path with MVTV_FOLD_COMMIT=1)
+    cases = [  # dims, n, mode, lambda, max_passes, preconditioner, world, comm ("fold": the default peer path, commits folded into the reducing kernels; "peer": MVTV_FOLD_COMMIT=0)
         ([24, 22], 3000, "rcpp", 1.0, 8, C1, 2, "peer"), ([24, 22], 3000, "cpp", 3.0, 0, J, 2, "peer"),
         ([24, 23], 3000, "rcpp", 1.0, 6, C1, 3, "peer"), ([24, 22], 3000, "rcpp", 1.0, 6, C1, 2, "nccl"),
         ([8, 8, 9], 2000, "rcpp", 0.7, 5, C1, 2, "peer"), ([8, 8, 9], 2000, "rcpp", 0.7, 5, J, 3, "peer"),
@@ -56,9 +56,10 @@ def main():
         cases += [([6, 4], 200, "rcpp", 1.0, 4, C1, 4, comm), ([10, 5], 300, "cpp", 2.0, 0, J, 4, comm), ([4, 4, 4], 300, "rcpp", 0.7, 3, C1, 4, comm),
                   ([3, 3, 3, 3], 300, "rcpp", 1.0, 3, J, 3, comm), ([7, 5], 100, "py", 0.8, 4, C1, 2, comm), ([2, 8], 50, "rcpp", 0.3, 4, C1, 4, comm),
                   ([1, 6], 40, "cpp", 1.5, 0, C1, 3, comm), ([16, 7], 5, "rcpp", 1.0, 3, C1, 3, comm)]
-    for comm in ("peer", "fold"):          # the opt-in kernels that have a multi-GPU path (9th field: extra environment)
-        cases += [([12, 12, 12], 1500, "rcpp", 0.7, 3, C1, 2, comm, {"MVTV_STEP3D": "shfl"}), ([66, 4, 9], 2000, "rcpp", 1.0, 2, C1, 2, comm, {"MVTV_STEP3D": "hyb"}),
-                  ([8, 8, 8], 600, "rcpp", 0.7, 3, J, 3, comm, {"MVTV_STEP3D": "hyb", "MVTV_STEP3D_CFG": "1"}), ([24, 23], 3000, "rcpp", 1.0, 4, C1, 3, comm, {"MVTV_INIT2D": "1"})]
+    for comm in ("peer", "fold"):          # the 3-D strip kernels on even widths, the ring on every width (9th field: extra environment)
+        cases += [([12, 12, 12], 1500, "rcpp", 0.7, 3, C1, 2, comm), ([66, 4, 9], 2000, "rcpp", 1.0, 2, C1, 2, comm),
+                  ([8, 8, 8], 600, "rcpp", 0.7, 3, J, 3, comm), ([12, 12, 12], 1500, "rcpp", 0.7, 3, C1, 2, comm, {"MVTV_STEP": "ring"}),
+                  ([24, 22], 3000, "rcpp", 1.0, 4, mv.PRECOND_CHEB3, 3, comm), ([24, 22], 3000, "rcpp", 1.0, 4, mv.PRECOND_AUTO, 2, comm)]
     if quick:
         cases = [cases[0], cases[3], cases[4], cases[9]]
     fail = 0
@@ -75,9 +76,9 @@ def main():
         os.environ.pop("MVTV_FOLD_COMMIT", None)
         if comm == "nccl":
             os.environ["MVTV_COMM"] = "nccl"
-        elif comm == "fold":
-            os.environ["MVTV_FOLD_COMMIT"] = "1"
-        for k in ("MVTV_STEP3D", "MVTV_STEP3D_CFG", "MVTV_INIT2D"):
+        elif comm == "peer":
+            os.environ["MVTV_FOLD_COMMIT"] = "0"   # separate commit launches (the default folds them into the reducing kernels)
+        for k in ("MVTV_STEP",):
             os.environ.pop(k, None)
         os.environ.update(extra)
         uid = mv.nccl_unique_id()
@@ -115,8 +116,7 @@ def main():
             "ok  " if good else "FAIL", dims, world, mode, precond, comm, (" " + str(extra)) if extra else "", d["cg_step"], results[0][2], ref["counter"], results[0][3], results[0][5], err), flush=True)
     os.environ.pop("MVTV_COMM", None)
     os.environ.pop("MVTV_FOLD_COMMIT", None)
-    for k in ("MVTV_STEP3D", "MVTV_STEP3D_CFG", "MVTV_INIT2D"):
-        os.environ.pop(k, None)
+    os.environ.pop("MVTV_STEP", None)
     print("emu_multi: %d failure(s)" % fail)
     return 1 if fail else 0
 

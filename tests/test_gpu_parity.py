@@ -430,10 +430,11 @@ def test_mbs_cv_driver(mv):
     final = ref_path(x, y)
     mean_mses = mse_mat.mean(axis=1)
     best = int(np.argmin(mean_mses))
-    assert np.allclose(out["cv.mse_mat"], mse_mat, rtol=1e-7, atol=1e-10)
+    # the driver's operators are delta-scaled: the library picks cg_rtol = 1e-14 for them, which keeps the 1e-9 bar
+    assert np.allclose(out["cv.mse_mat"], mse_mat, rtol=1e-9, atol=1e-11)
     assert out["lambda_minmse_ind"] == best + 1
-    assert np.abs(out["theta_hat"] - final[best]["theta"]).max() <= 1e-8
-    assert np.abs(out["fitted"] - final[best]["fitted"]).max() <= 1e-8
+    assert np.abs(out["theta_hat"] - final[best]["theta"]).max() <= FP64_TOL
+    assert np.abs(out["fitted"] - final[best]["fitted"]).max() <= FP64_TOL
     assert [mm["lambda"] for mm in out["models"]] == list(lambdas)
     assert np.allclose(out["residuals"], y - out["fitted"])
     # folds = 1 with the default grid: runs end to end, picks the smallest training MSE
@@ -510,56 +511,94 @@ def test_gather_kernel_cross_check(mv, monkeypatch):
         assert np.abs(a["u"] - b["u"]).max() <= 1e-11
 
 
-def test_step2d_kernel_cross_check(mv, monkeypatch):
-    """k_cg_step (shared-memory ring) and k_cg_step2d (warp shuffles, no shared memory; its preconditioner variant never
-    reads diag(c)) are two implementations of the fused CG direction + SpMV on 2-D meshes: same passes, theta within
-    1e-10 of each other and within 1e-9 of the oracle, on widths that are / are not multiples of the 64- and 128-vertex
-    strips, for both preconditioners; odd widths fall back to k_cg_step."""
-    for dims, n in ([100, 37], 3000), ([66, 5], 400), ([2, 9], 60), ([258, 33], 9000), ([130, 64], 5000):
-        x, y = synth(80 + dims[0], n, 2, 0.0, 1.0, 0.5)
+def test_strip_vs_ring_kernel_cross_check(mv, monkeypatch):
+    """The strip kernels (k_cg_step2d / k_cg_step3d: warp shuffles, no shared memory, diag(c) derived from dinv, update
+    fused with the first preconditioner pass, Horner passes for degree >= 2) and k_cg_step (shared-memory ring, separate
+    update; MVTV_STEP=ring) are two implementations of the x-update: same passes, theta within 1e-10 of each other and within
+    1e-9 of the oracle, on widths that are / are not multiples of the 64- and 128-vertex strips, for Jacobi and every
+    polynomial degree; odd widths and 4-D meshes run k_cg_step."""
+    cases = [([100, 37], 3000), ([66, 5], 400), ([2, 9], 60), ([258, 33], 9000), ([130, 64], 5000),
+             ([12, 12, 12], 2000), ([66, 5, 7], 1500), ([130, 33, 6], 9000)]
+    for dims, n in cases:
+        p = len(dims)
+        x, y = synth(80 + dims[0], n, p, 0.0, 1.0, 0.5)
         axes = po.mesh_axes(x, dims, po.MODE_RCPP)
-        for precond in (mv.PRECOND_CHEB1, mv.PRECOND_JACOBI):
-            res = {}
-            for which in ("shfl", "smem"):
-                monkeypatch.setenv("MVTV_STEP2D", which)
-                with mv.Plan(dims) as pl:
-                    assert pl.describe()["cg_step"] == ("k_cg_step2d" if which == "shfl" else "k_cg_step")
-                    pl.set_points(x, y, axes)
-                    res[which] = pl.solve(0.8, mode="rcpp", max_passes=40, precond=precond)
-            monkeypatch.delenv("MVTV_STEP2D", raising=False)
-            assert res["shfl"]["passes"] == res["smem"]["passes"]
-            assert np.abs(res["shfl"]["theta"] - res["smem"]["theta"]).max() <= 1e-10
-        ref = co.mbs_one(x, y, dims, axes, 0.8, mode=co.MODE_RCPP, max_passes=40)
-        assert np.abs(res["shfl"]["theta"] - ref["theta"]).max() <= FP64_TOL
-    monkeypatch.delenv("MVTV_STEP2D", raising=False)
+        variant = mv.VARIANT_REFERENCE if (p == 2 or len(set(dims)) == 1) else mv.VARIANT_INTENDED   # reference operator: cubic meshes only
+        strip = "k_cg_step2d" if p == 2 else "k_cg_step3d"
+        monkeypatch.setenv("MVTV_STEP", "ring")
+        ring = {}
+        with mv.Plan(dims, variant=variant) as pl:
+            assert pl.describe()["cg_step"] == "k_cg_step" and pl.describe()["max_degree"] == 1
+            pl.set_points(x, y, axes)
+            for precond in (mv.PRECOND_JACOBI, mv.PRECOND_CHEB1):
+                ring[precond] = pl.solve(0.8, mode="rcpp", max_passes=30, precond=precond)
+        monkeypatch.delenv("MVTV_STEP", raising=False)
+        ref = co.mbs_one(x, y, dims, axes, 0.8, mode=co.MODE_RCPP, max_passes=30, variant=variant)
+        iters = []
+        with mv.Plan(dims, variant=variant) as pl:
+            d = pl.describe()
+            assert d["cg_step"] == strip and d["cg_prec_words"] == 3 and d["max_degree"] == 4 and d["fused_update"] == 1
+            pl.set_points(x, y, axes)
+            for precond in (mv.PRECOND_JACOBI, mv.PRECOND_CHEB1, mv.PRECOND_CHEB2, mv.PRECOND_CHEB3, mv.PRECOND_CHEB4):
+                out = pl.solve(0.8, mode="rcpp", max_passes=30, precond=precond)
+                assert out["passes"] == ref["passes"], (dims, precond)
+                assert np.abs(out["theta"] - ref["theta"]).max() <= FP64_TOL, (dims, precond)
+                if precond in ring:
+                    assert out["inner_iters"] == ring[precond]["inner_iters"]
+                    assert np.abs(out["theta"] - ring[precond]["theta"]).max() <= 1e-10
+                iters.append(out["inner_iters"])
+        assert iters[1] < iters[0] or iters[0] < 50 * 30
     with mv.Plan([33, 20]) as pl:                       # odd width: rows are not 16-byte aligned
         d = pl.describe()
-        assert d["cg_step"] == "k_cg_step" and d["cg_prec_words"] == 4
+        assert d["cg_step"] == "k_cg_step" and d["cg_prec_words"] == 4 and d["fused_update"] == 0
     with mv.Plan([32, 20]) as pl:
         d = pl.describe()
-        assert d["cg_step"] == "k_cg_step2d" and d["cg_prec_words"] == 3 and d["collectives"] == "none"
+        assert d["cg_step"] == "k_cg_step2d" and d["collectives"] == "none"
     with mv.Plan([8, 8, 8]) as pl:
+        assert pl.describe()["cg_step"] == "k_cg_step3d"
+    with mv.Plan([6, 6, 6, 6]) as pl:
         assert pl.describe()["cg_step"] == "k_cg_step"
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MVTV_EXPERIMENTAL") != "1",
-                    reason="k_cg_step3d is opt-in (MVTV_STEP3D=shfl) and not yet validated on a GPU: set MVTV_EXPERIMENTAL=1")
-def test_step3d_kernel_cross_check_experimental(mv, monkeypatch):
-    """EXPERIMENTAL k_cg_step3d (cg_step3d.cuh) and k_cg_step3dh (cg_step3dh.cuh) vs k_cg_step on 3-D meshes; see
-    tools/step3d_probe.py."""
-    names = {"shfl": "k_cg_step3d", "hyb": "k_cg_step3dh", "smem": "k_cg_step"}
-    for dims, n in ([12, 12, 12], 2000), ([66, 5, 7], 1500), ([130, 33, 6], 9000):
-        x, y = synth(90 + dims[0], n, 3, 0.0, 1.0, 0.5)
-        axes = po.mesh_axes(x, dims, po.MODE_RCPP)
-        res = {}
-        for which in ("shfl", "hyb", "smem"):
-            monkeypatch.setenv("MVTV_STEP3D", which)
-            variant = mv.VARIANT_REFERENCE if len(set(dims)) == 1 else mv.VARIANT_INTENDED   # reference operator: cubic meshes only
-            with mv.Plan(dims, variant=variant) as pl:
-                assert pl.describe()["cg_step"] == names[which]
-                pl.set_points(x, y, axes)
-                res[which] = pl.solve(0.8, mode="rcpp", max_passes=30, precond=mv.PRECOND_CHEB1)
-        monkeypatch.delenv("MVTV_STEP3D", raising=False)
-        for which in ("shfl", "hyb"):
-            assert res[which]["passes"] == res["smem"]["passes"]
-            assert np.abs(res[which]["theta"] - res["smem"]["theta"]).max() <= 1e-10
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs at the sizes bench.py times (VERDICT r1: "no config above 32^2 is compared with the oracle at its size")
+# ---------------------------------------------------------------------------------------------
+def _bench_points(n, p, seed=117):
+    rng = np.random.default_rng(seed)          # bench.py's generator
+    x = rng.random((n, p))
+    f = np.prod(x > 0.5, axis=1) * 1.0 + 0.5 * np.prod(x < 0.2, axis=1)
+    return x, f + 0.5 * rng.standard_normal(n)
+
+
+def _fullsize_case(mv, dims, n, passes, preconds, lam=1.0):
+    import os
+    p = len(dims)
+    x, y = _bench_points(n, p)
+    axes = [np.linspace(0.0, 1.0, d) for d in dims]
+    nth = len(os.sched_getaffinity(0))
+    ref = co.mbs_one(x, y, dims, axes, lam, mode=co.MODE_RCPP, max_passes=passes, solver=co.SOLVER_PCG, cg_rtol=1e-13,
+                     nthreads=nth)
+    with mv.Plan(dims) as pl:
+        pl.set_points(x, y, axes)
+        for precond in preconds:
+            out = pl.solve(lam, mode="rcpp", max_passes=passes, precond=precond, want_u=True, want_fitted=False,
+                           raise_on_nonconvergence=False)
+            assert out["counter"] == ref["counter"] and out["passes"] == ref["passes"], (dims, precond)
+            assert np.abs(out["theta"] - ref["theta"]).max() <= FP64_TOL, (dims, precond, np.abs(out["theta"] - ref["theta"]).max())
+            assert np.abs(out["u"] - ref["u"]).max() <= 1e-8, (dims, precond)
+            assert out["rho"] == ref["rho"]
+
+
+def test_config2_full_size_parity(mv):
+    """BASELINE configs[1] at its stated size (4096^2, n = 2^24, fp64, RCPP mode, lambda = 1): 12 passes of the CUDA path
+    against oracle/c (PCG to 1e-13) -- identical passes / Counter, theta <= 1e-9, u <= 1e-8, rho equal -- for Jacobi, the
+    degree-1 polynomial and the default (AUTO)."""
+    _fullsize_case(mv, [4096, 4096], 1 << 24, 12, (mv.PRECOND_JACOBI, mv.PRECOND_CHEB1, mv.PRECOND_AUTO))
+
+
+def test_config3_bounded_parity(mv):
+    """BASELINE configs[2] (3-D, n = N/2 points per vertex, reference operator) on a 256^3 mesh, 3 passes, and configs[3]
+    (4-D, n = N) on a 48^4 mesh, 3 passes: same checks.  The 512^3 / 96^4 meshes themselves are checked by
+    tools/fullsize_parity.py (minutes of CPU oracle time; log under profiles/)."""
+    _fullsize_case(mv, [256, 256, 256], 1 << 23, 3, (mv.PRECOND_CHEB1, mv.PRECOND_AUTO))
+    _fullsize_case(mv, [48, 48, 48, 48], 48 ** 4, 3, (mv.PRECOND_CHEB1, mv.PRECOND_AUTO))
