@@ -33,7 +33,7 @@ k_cg_updprec2d(const __grid_constant__ DimTab dt, const __grid_constant__ Stenci
   const T alpha = (T)(a.S[2 * cur] / a.S[CS_PQ]);
   const T *__restrict__ r_in = cur ? a.r2 : a.r;     // cg_rcur
   T *__restrict__ r_out = cur ? a.r : a.r2;
-  T *__restrict__ zo = a.w_out_scr ? cg_wscratch(a, it, true) : a.z;   // first Horner pass of a degree >= 2 polynomial
+  T *__restrict__ zo = cg_wsel(a, a.w_out_scr, it, true);   // first Horner pass of a degree >= 2 polynomial
   const T *__restrict__ p = a.pbuf[cur ^ 1];          // the direction k_cg_step2d<STEP_Z> just wrote
   const T *__restrict__ q = a.q;
   const T *__restrict__ dinv = a.dinv;

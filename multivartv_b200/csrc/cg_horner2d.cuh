@@ -22,8 +22,8 @@ k_cg_horner2d(const __grid_constant__ DimTab dt, const __grid_constant__ Stencil
               const RedBuf rb, const int zchunk) {
   if (cg_done(a.S, a.rtol2)) return;
   const int it = (int)a.S[CS_ITERS];
-  const T *__restrict__ w_in = a.w_in_scr ? cg_wscratch(a, it, false) : a.z;
-  T *__restrict__ w_out = a.w_out_scr ? cg_wscratch(a, it, false) : a.z;
+  const T *__restrict__ w_in = cg_wsel(a, a.w_in_scr, it, false);
+  T *__restrict__ w_out = cg_wsel(a, a.w_out_scr, it, false);
   const double c_lo = a.pc0, c_hi = a.pc1;
   const int final_pass = a.final_pass;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

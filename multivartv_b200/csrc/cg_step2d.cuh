@@ -69,7 +69,7 @@ k_cg_step2d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   const T *__restrict__ p_in = a.pbuf[cur];
   T *__restrict__ p_out = a.pbuf[cur ^ 1];
   const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : cg_rcur(a, it);
-  T *__restrict__ zo = a.w_out_scr ? cg_wscratch(a, it, false) : a.z;   // STEP_PREC output (first Horner pass of a degree >= 2 polynomial)
+  T *__restrict__ zo = cg_wsel(a, a.w_out_scr, it, false);   // STEP_PREC output (first Horner pass of a degree >= 2 polynomial)
   const T *__restrict__ dinv = a.dinv;
   const T rhoM = (T)a.rhoM;
 

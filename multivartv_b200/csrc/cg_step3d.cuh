@@ -3,6 +3,9 @@
 // 1.02 ms, profiles/r2_call1_step3d_probe.log).  Same modes, arguments, reduction epilogue and ghost-plane protocol as
 // k_cg_step / k_cg_step2d, plus the two modes of the polynomial preconditioner of degree >= 2 and of the fused update:
 //   STEP_HORNER   w_out = D^-1 M w_in + pc0 * D^-1 r          (pass k >= 2 of the Horner form; reads w_in, dinv, r: 4 N words)
+//   STEP_INIT     the CG initialisation of k_cg_init in marching form: r = b - M theta, theta_old = theta, r.z (z = D^-1 r), r.r,
+//                 b.b with b = Oty + rho (D^T alpha + uscale D^T u) never stored (8 N words; theta's halo rows come out of L1 / L2
+//                 instead of 27 gathers per vertex)
 //   STEP_UPDPREC  theta += alpha p ; r_new = r - alpha q (out of place) ; w_out = pc0 z0 + pc1 D^-1 M z0, z0 = D^-1 r_new
 //                 (k_cg_update fused with the first preconditioner pass: reads theta, p, r, q, dinv, writes theta, r, w:
 //                 8 N words instead of 6 N + 3 N; r_new is also formed on the halo rows / planes, which needs q there)
@@ -28,7 +31,7 @@ template <typename T, typename Cfg, int MODE>
 __global__ void __launch_bounds__(Cfg::NT, (Cfg::MINB > 0 ? Cfg::MINB : 1))
 k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab st, const CgArgs<T> a,
             const RedBuf rb, const int zchunk) {
-  if (cg_done(a.S, a.rtol2)) return;
+  if (MODE != STEP_INIT && cg_done(a.S, a.rtol2)) return;   // STEP_INIT starts a solve: the scalars are the previous solve's
   constexpr int RY = Cfg::RY, NR = Cfg::RY + 2;
   constexpr bool POLY = (MODE == STEP_PREC || MODE == STEP_HORNER || MODE == STEP_UPDPREC);   // writes a preconditioner pass
   constexpr bool NOC = (Cfg::NOC && MODE == STEP_PREC) || MODE == STEP_HORNER || MODE == STEP_UPDPREC;
@@ -36,18 +39,18 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int it = (int)a.S[CS_ITERS];
   const int cur = it & 1;
-  const bool first = POLY ? true : (it == 0);   // "first": no p_old term
+  const bool first = (POLY || MODE == STEP_INIT) ? true : (it == 0);   // "first": no p_old term
   const bool stage_c = (MODE == STEP_UPDPREC) || !first;   // third staged array: p_old (JACOBI, Z) or q (UPDPREC)
   const T beta = first ? T(0) : (T)(a.S[2 * cur] / a.S[2 * (cur ^ 1)]);
   const T alpha = (MODE == STEP_UPDPREC) ? (T)(a.S[2 * cur] / a.S[CS_PQ]) : T(0);
   const T *__restrict__ p_in = (MODE == STEP_UPDPREC) ? a.q : a.pbuf[cur];
   T *__restrict__ p_out = a.pbuf[cur ^ 1];
   const T *__restrict__ rcur = cg_rcur(a, it);
-  const T *__restrict__ w_in = a.w_in_scr ? cg_wscratch(a, it, false) : a.z;
-  const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : ((MODE == STEP_HORNER) ? w_in : rcur);
+  const T *__restrict__ w_in = cg_wsel(a, a.w_in_scr, it, false);
+  const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : ((MODE == STEP_HORNER) ? w_in : ((MODE == STEP_INIT) ? a.x : rcur));
   T *__restrict__ r_out = (MODE == STEP_UPDPREC) ? (cur ? a.r : a.r2) : nullptr;
   const T *__restrict__ p_dir = a.pbuf[cur ^ 1];   // STEP_UPDPREC: the direction the step kernel just wrote
-  T *__restrict__ zo = a.w_out_scr ? cg_wscratch(a, it, MODE == STEP_UPDPREC) : a.z;
+  T *__restrict__ zo = cg_wsel(a, a.w_out_scr, it, MODE == STEP_UPDPREC);
   const T *__restrict__ dinv = a.dinv;
   const T rhoM = (T)a.rhoM;
 
@@ -73,21 +76,46 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
 #pragma unroll
   for (int j = 0; j < RY; ++j) valid[j] = xvalid && (y0 + j < m1);
 
-  const int zc0 = blockIdx.y * zchunk;
+  // chunk of the marching axis this CTA owns.  CTAs are scheduled in blockIdx order: on several GPUs the two chunks that
+  // wait for a neighbour's ghost planes go last, so that no CTA spins on a flag while interior work is still queued
+  const int nchunk = (int)gridDim.y;
+  int chunk = (int)blockIdx.y;
+  if (a.peer && nchunk > 2) chunk = (chunk < nchunk - 2) ? chunk + 1 : (chunk == nchunk - 2 ? 0 : nchunk - 1);
+  const int zc0 = chunk * zchunk;
   const int zc1 = min(zc0 + zchunk, dt.nz);
   const int zlo = dt.has_lo ? -1 : 0;
   const int zhi = dt.has_hi ? dt.nz : dt.nz - 1;
   const int zfirst = zc0 - 1, zlast = zc1;
-  if (a.peer) {  // the neighbours fill our ghost planes of r (z) directly: wait for the version this launch needs
+  const bool ghost_lo = (zc0 == 0 && dt.has_lo), ghost_hi = (zc1 == dt.nz && dt.has_hi);   // this CTA reads ghost planes
+  if (a.peer) {  // the neighbours fill our ghost planes directly: wait for the versions this launch needs
     if (tid == 0) {
-      const unsigned long long need = (MODE == STEP_Z) ? a.seq_zhalo : a.seq_halo;
-      const unsigned long long *fp = (MODE == STEP_Z) ? a.peer->zflag_from_prev : a.peer->hflag_from_prev;
-      const unsigned long long *fn = (MODE == STEP_Z) ? a.peer->zflag_from_next : a.peer->hflag_from_next;
-      if (zc0 == 0 && dt.has_lo) peer_spin(fp, need, a.peer->error);
-      if (zc1 == dt.nz && dt.has_hi) peer_spin(fn, need, a.peer->error);
+      if (MODE == STEP_JACOBI || MODE == STEP_PREC || MODE == STEP_UPDPREC) {   // r (STEP_UPDPREC: posted by the CG initialisation,
+        if (ghost_lo) peer_spin(a.peer->hflag_from_prev, a.seq_halo, a.peer->error);   // kept up to date locally afterwards)
+        if (ghost_hi) peer_spin(a.peer->hflag_from_next, a.seq_halo, a.peer->error);
+      }
+      if (MODE == STEP_Z || MODE == STEP_HORNER || MODE == STEP_UPDPREC) {      // z, w_{k-1}, q
+        if (ghost_lo) peer_spin(a.peer->zflag_from_prev, a.seq_zin, a.peer->error);
+        if (ghost_hi) peer_spin(a.peer->zflag_from_next, a.seq_zin, a.peer->error);
+      }
     }
     __syncthreads();
   }
+  // where this rank's boundary planes of the output go in the neighbours' slabs (nullptr: nothing to export)
+  T *exp_prev = nullptr, *exp_next = nullptr;
+  if (a.peer) {
+    if (POLY) {
+      const int wi = cg_widx(a.w_out_scr, it, MODE == STEP_UPDPREC);
+      exp_prev = dt.has_lo ? (T *)a.peer->wghost_at_prev[wi] : nullptr;
+      exp_next = dt.has_hi ? (T *)a.peer->wghost_at_next[wi] : nullptr;
+    } else if (MODE == STEP_INIT) {        // r's ghost planes at the neighbours
+      exp_prev = dt.has_lo ? (T *)a.peer->rghost_at_prev : nullptr;
+      exp_next = dt.has_hi ? (T *)a.peer->rghost_at_next : nullptr;
+    } else if (MODE == STEP_Z && a.r2) {   // fused update: the neighbours form r - alpha q on their ghost planes
+      exp_prev = dt.has_lo ? (T *)a.peer->qghost_at_prev : nullptr;
+      exp_next = dt.has_hi ? (T *)a.peer->qghost_at_next : nullptr;
+    }
+  }
+  bool stored_peer = false;
   // NOC: boundary class bits of this lane's outputs within a plane (bit 0: axis 0, bit 1: axis 1)
   int cls[RY][2];
 #pragma unroll
@@ -98,14 +126,14 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
 
   // raw inputs of the next plane, in flight while the current one is consumed
   // rcc / rdd: own-row extras -- diag(c) (!NOC) ; dinv and r (STEP_HORNER) ; theta and p (STEP_UPDPREC)
-  T ra[NR][2], rb_[NR][2], rc[NR][2], rcc[RY][2], rdd[RY][2], ha[NR], hb[NR], hc[NR];
+  T ra[NR][2], rb_[NR][2], rc[NR][2], rcc[RY][2], rdd[RY][2], re1[RY][2], re2[RY][2], re3[RY][2], ha[NR], hb[NR], hc[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     ra[r][0] = ra[r][1] = rb_[r][0] = rb_[r][1] = rc[r][0] = rc[r][1] = T(0);
     ha[r] = hb[r] = hc[r] = T(0);
   }
 #pragma unroll
-  for (int j = 0; j < RY; ++j) rcc[j][0] = rcc[j][1] = rdd[j][0] = rdd[j][1] = T(0);
+  for (int j = 0; j < RY; ++j) rcc[j][0] = rcc[j][1] = rdd[j][0] = rdd[j][1] = re1[j][0] = re1[j][1] = re2[j][0] = re2[j][1] = re3[j][0] = re3[j][1] = T(0);
   auto load_plane = [&](int zz) {
     if (zz > zlast) return;
     const int zs = min(max(zz, zlo), zhi);
@@ -126,9 +154,10 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
       for (int j = 0; j < RY; ++j)
         if (valid[j]) {
           const long long ob = (long long)(zz + 1) * dt.plane + (long long)(y0 + j) * m0 + x;
-          if (!NOC) ld2(a.c + ob, rcc[j]);
+          if (!NOC || MODE == STEP_INIT) ld2(a.c + ob, rcc[j]);
           if (MODE == STEP_HORNER) { ld2(dinv + ob, rcc[j]); ld2(rcur + ob, rdd[j]); }
           if (MODE == STEP_UPDPREC) { ld2(a.x + ob, rcc[j]); ld2(p_dir + ob, rdd[j]); }
+          if (MODE == STEP_INIT) { ld2(dinv + ob, rdd[j]); ld2(a.oty + ob, re1[j]); ld2(a.v1 + ob, re2[j]); ld2(a.v2 + ob, re3[j]); }
         }
     }
   };
@@ -138,7 +167,7 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   for (int j = 0; j < RY; ++j)
 #pragma unroll
     for (int k = 0; k < 2; ++k) A0[j][k] = A1[j][k] = A2[j][k] = pcp[j][k] = cqp[j][k] = rcp[j][k] = dcp[j][k] = T(0);
-  double red[2] = {0.0, 0.0};   // [1]: r.r of STEP_UPDPREC
+  double red[3] = {0.0, 0.0, 0.0};   // [1]: r.r of STEP_UPDPREC / STEP_INIT, [2]: b.b of STEP_INIT
 
   load_plane(zfirst);
   for (int zz = zfirst; zz <= zlast; ++zz) {
@@ -167,8 +196,9 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
     for (int j = 0; j < RY; ++j)
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        rown[j][k] = (MODE == STEP_HORNER) ? rdd[j][k] : ra[j + 1][k];
-        down[j][k] = (MODE == STEP_HORNER) ? rcc[j][k] : rb_[j + 1][k];
+        rown[j][k] = (MODE == STEP_HORNER) ? rdd[j][k]
+                     : ((MODE == STEP_INIT) ? re1[j][k] + (T)a.rho * (re2[j][k] + (T)a.uscale * re3[j][k]) : ra[j + 1][k]);   // STEP_INIT: b
+        down[j][k] = (MODE == STEP_HORNER) ? rcc[j][k] : ((MODE == STEP_INIT) ? rdd[j][k] : rb_[j + 1][k]);
         cown[j][k] = rcc[j][k];
       }
     if (MODE == STEP_UPDPREC && zz >= zc0 && zz < zc1) {   // theta and r_new of the own rows of an own plane
@@ -180,6 +210,12 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
           st2(a.x + ob, rcc[j][0] + alpha * rdd[j][0], rcc[j][1] + alpha * rdd[j][1]);
           red[1] += (double)ra[j + 1][0] * (double)ra[j + 1][0] + (double)ra[j + 1][1] * (double)ra[j + 1][1];
         }
+    }
+    if (MODE == STEP_UPDPREC && ((zz < 0 && ghost_lo) || (zz >= dt.nz && ghost_hi))) {
+      // several GPUs: r_new on the ghost planes, the same arithmetic as on the rank that owns them -- r needs no exchange
+#pragma unroll
+      for (int j = 0; j < RY; ++j)
+        if (valid[j]) st2(r_out + (long long)(zz + 1) * dt.plane + (long long)(y0 + j) * m0 + x, ra[j + 1][0], ra[j + 1][1]);
     }
     load_plane(zz + 1);                                  // the registers are free: the next plane goes in flight
     {
@@ -228,7 +264,13 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const T pv = pcp[j][k];
-          if (MODE == STEP_HORNER) {   // w_k = D^-1 M w_{k-1} + pc0 z0,  D^-1 M w = w + dinv*rhoM*(K w - diag(K) w)
+          if (MODE == STEP_INIT) {     // r = b - (c theta + rhoM K theta)
+            const T rv = rcp[j][k] - (cqp[j][k] * pv + rhoM * A0[j][k]);
+            outv[k] = rv;
+            red[0] += (double)rv * (double)(rv * dcp[j][k]);
+            red[1] += (double)rv * (double)rv;
+            red[2] += (double)rcp[j][k] * (double)rcp[j][k];
+          } else if (MODE == STEP_HORNER) {   // w_k = D^-1 M w_{k-1} + pc0 z0,  D^-1 M w = w + dinv*rhoM*(K w - diag(K) w)
             const T dk = (T)st.diagK[cls[j][k] | bz];
             const T zv = pv + rhoM * dcp[j][k] * (A0[j][k] - dk * pv) + (T)a.pc0 * (dcp[j][k] * rcp[j][k]);
             outv[k] = zv;
@@ -250,15 +292,12 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
             red[0] += (double)pv * (double)qv;
           }
         }
-        if (POLY) {
-          st2(zo + ob, outv[0], outv[1]);
-          if (MODE == STEP_PREC && a.peer) {  // fill the neighbours' ghost planes of z
-            const long long q = (long long)(y0 + j) * m0 + x;
-            if (zz - 1 == 0 && dt.has_lo) { st2((T *)a.peer->zghost_at_prev + q, outv[0], outv[1]); __threadfence_system(); }
-            if (zz - 1 == dt.nz - 1 && dt.has_hi) { st2((T *)a.peer->zghost_at_next + q, outv[0], outv[1]); __threadfence_system(); }
-          }
-        } else {
-          st2(a.q + ob, outv[0], outv[1]);
+        st2((POLY ? zo : (MODE == STEP_INIT ? a.r : a.q)) + ob, outv[0], outv[1]);
+        if (MODE == STEP_INIT) st2(a.xold + ob, pcp[j][0], pcp[j][1]);
+        {  // several GPUs: the boundary planes also go straight into the neighbours' ghost planes
+          const long long q = (long long)(y0 + j) * m0 + x;
+          if (exp_prev && zz - 1 == 0) { st2(exp_prev + q, outv[0], outv[1]); stored_peer = true; }
+          if (exp_next && zz - 1 == dt.nz - 1) { st2(exp_next + q, outv[0], outv[1]); stored_peer = true; }
         }
       }
     }
@@ -275,41 +314,79 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
         dcp[j][k] = down[j][k];
       }
   }
+  if (stored_peer) __threadfence_system();   // one fence per thread, before the CTA reports to the grid reduction
   double *S = a.S, *raw = a.raw;
   const PeerTab *peer = a.peer;
-  const unsigned long long sr = a.seq_red, sz = a.seq_zhalo;
-  const int fold = a.fold;
-  if (MODE == STEP_UPDPREC) {   // one GPU: {r.z, r.r} of the next parity, iteration count advances
-    const int fin = a.final_pass;
-    grid_reduce<2, 2>(red, rb, [S, fin](const double (&res)[2]) {
-      if (fin) cg_commit_update(S, res);
-      else cg_commit_update_prec(S, res + 1);   // r.z comes from the last Horner pass
+  const unsigned long long sr = a.seq_red, szo = a.seq_zout;
+  const int fold = a.fold, fin = a.final_pass;
+  const bool post_z = peer && (POLY || (MODE == STEP_Z && a.r2));   // this launch exported boundary planes
+  // the epilogue runs in ONE thread after every CTA of the grid has finished (and fenced) its stores
+  auto signal_z = [peer, szo, post_z]() {
+    if (!post_z) return;
+    __threadfence_system();
+    if (peer->has_lo) st_release_sys(peer->zflag_at_prev, szo);
+    if (peer->has_hi) st_release_sys(peer->zflag_at_next, szo);
+  };
+  if (MODE == STEP_INIT) {      // {r.z, r.r, b.b}; r's ghost planes are posted on the halo flags
+    const unsigned long long sh = a.seq_halo;
+    grid_reduce<3, 3>(red, rb, [S, raw, peer, sr, sh, fold](const double (&res)[3]) {
+      if (peer) {
+        __threadfence_system();
+        if (peer->has_lo) st_release_sys(peer->hflag_at_prev, sh);
+        if (peer->has_hi) st_release_sys(peer->hflag_at_next, sh);
+        peer_post(*peer, sr, res, 3);
+        if (fold) {   // what k_cg_peer_commit_init does
+          double v[3];
+          peer_wait_sum(*peer, sr, v, 3);
+          cg_commit_init(S, v);
+        }
+      } else if (raw) { raw[0] = res[0]; raw[1] = res[1]; raw[2] = res[2]; }
+      else cg_commit_init(S, res);
     });
     return;
   }
-  if (MODE == STEP_HORNER || (MODE == STEP_PREC && !a.final_pass)) {   // one GPU
-    if (!a.final_pass) return;
-    double r1[1] = {red[0]};
-    grid_reduce<1, 1>(r1, rb, [S](const double (&res)[1]) { cg_commit_rz(S, res); });
+  if (MODE == STEP_UPDPREC) {   // {r.z, r.r} of the next parity, the iteration count advances (several GPUs: folded commits only)
+    double r2[2] = {red[0], red[1]};
+    grid_reduce<2, 2>(r2, rb, [S, peer, sr, fin, signal_z](const double (&res)[2]) {
+      double v[2] = {res[0], res[1]};
+      if (peer) {
+        signal_z();
+        peer_post(*peer, sr, res, 2);
+        peer_wait_sum(*peer, sr, v, 2);
+      }
+      if (fin) cg_commit_update(S, v);
+      else cg_commit_update_prec(S, v + 1);   // r.z comes from the last Horner pass
+    });
     return;
   }
   double r1[1] = {red[0]};
-  grid_reduce<1, 1>(r1, rb, [S, raw, peer, sr, sz, fold](const double (&res)[1]) {
+  if (MODE == STEP_HORNER || MODE == STEP_PREC) {
+    if (!fin && !peer) return;   // one GPU, not the last pass: nothing to reduce, nobody to signal
+    grid_reduce<1, 1>(r1, rb, [S, raw, peer, sr, fold, fin, signal_z](const double (&res)[1]) {
+      if (peer) {
+        signal_z();
+        if (!fin) return;
+        peer_post(*peer, sr, res, 1);
+        if (fold) {   // what k_cg_peer_commit_rz does
+          double v[1];
+          peer_wait_sum(*peer, sr, v, 1);
+          cg_commit_rz(S, v);
+        }
+      } else if (raw) raw[0] = res[0];
+      else cg_commit_rz(S, res);
+    });
+    return;
+  }
+  grid_reduce<1, 1>(r1, rb, [S, raw, peer, sr, fold, signal_z](const double (&res)[1]) {   // STEP_JACOBI / STEP_Z: p.q
     if (peer) {
-      if (MODE == STEP_PREC) {
-        __threadfence_system();
-        if (peer->has_lo) st_release_sys(peer->zflag_at_prev, sz);
-        if (peer->has_hi) st_release_sys(peer->zflag_at_next, sz);
-      }
+      signal_z();
       peer_post(*peer, sr, res, 1);
-      if (fold) {   // what k_cg_peer_commit_rz / k_cg_peer_commit_pq do
+      if (fold) {   // what k_cg_peer_commit_pq does
         double v[1];
         peer_wait_sum(*peer, sr, v, 1);
-        if (MODE == STEP_PREC) cg_commit_rz(S, v);
-        else S[CS_PQ] = v[0];
+        S[CS_PQ] = v[0];
       }
     } else if (raw) raw[0] = res[0];
-    else if (MODE == STEP_PREC) cg_commit_rz(S, res);
     else S[CS_PQ] = res[0];
   });
 }

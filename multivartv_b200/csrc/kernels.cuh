@@ -223,7 +223,13 @@ struct PeerTab {
   void *zghost_at_prev, *zghost_at_next;      // ... and of z (polynomial preconditioner)
   unsigned long long *zflag_at_prev, *zflag_at_next, *zflag_from_prev, *zflag_from_next;
   int *error;                                 // set when a wait times out (a peer died): results become NaN
+  // 3-D strip kernels (fused update, Horner passes): the neighbours' ghost planes of q and of the buffers a preconditioner
+  // pass may write -- PW_Z, PW_P0 / PW_P1 (the idle direction buffer), PW_Y.  All of them signal on the z flags, with one
+  // increasing event number per exchange (seq_zout of the producer = seq_zin of the consumer).
+  void *qghost_at_prev, *qghost_at_next;
+  void *wghost_at_prev[4], *wghost_at_next[4];
 };
+enum { PW_Z = 0, PW_P0 = 1, PW_P1 = 2, PW_Y = 3 };
 
 #ifdef MVTV_CUDA_EMU   // tests/cuda_emu: the kernel source compiled for the CPU emulator (ranks are host threads: host atomics)
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
@@ -303,12 +309,16 @@ struct CgArgs {
   T *z;            // polynomial preconditioner: z = P(D^-1 M) D^-1 r (ghosted slab)
   double pc0, pc1; // first Horner pass: w_1 = pc0*z0 + pc1*D^-1 M z0,  z0 = D^-1 r  (degree 1: w_1 = z)
   int prec;        // 0: Jacobi (z = D^-1 r formed on the fly), d >= 1: degree-d Chebyshev polynomial in D^-1 M
-  // degree >= 2 (Horner form, one stencil pass per degree): w ping-pongs between the z buffer and a scratch buffer, ending
-  // in z.  The scratch is the direction buffer that is idle between two step kernels -- pbuf[parity ^ 1] once the update has
-  // advanced the iteration count, pbuf[parity] inside the fused update (cg_wscratch) -- so q stays readable.
-  int w_out_scr = 0;         // this pass writes the scratch buffer (else z)
-  int w_in_scr = 0;          // pass k >= 2 reads w_{k-1} from the scratch buffer (else z):  w_k = D^-1 M w_{k-1} + pc0*z0
+  // degree >= 2 (Horner form, one stencil pass per degree): pass outputs rotate over the z buffer, X = the direction buffer
+  // that is idle between two step kernels -- pbuf[parity ^ 1] once the update has advanced the iteration count, pbuf[parity]
+  // inside the fused update (cg_wsel) -- and the extra buffer y, ending in z: [z], [X, z], [X, y, z], [z, X, y, z] for degree
+  // 1..4.  q stays readable, and on several GPUs no buffer is rewritten before the pass after next, i.e. not before the
+  // neighbour that reads its ghost planes has finished (its completion flag is what the pass in between waited for).
+  int w_out_scr = 0;         // buffer this pass writes: 0 = z, 1 = X, 2 = y
+  int w_in_scr = 0;          // buffer pass k >= 2 reads w_{k-1} from:  w_k = D^-1 M w_{k-1} + pc0*z0
   int final_pass = 1;        // the pass that produces z also reduces r.z
+  T *y = nullptr;
+  unsigned long long seq_zin = 0, seq_zout = 0;   // k_cg_step3d: z-flag event this launch needs / posts (see PeerTab)
   // fused update + first preconditioner pass (k_cg_updprec*): r is updated OUT OF PLACE, the buffer holding the
   // current residual is selected by the parity of the iterations performed (r2 == nullptr: r is updated in place)
   T *r2 = nullptr;
@@ -316,10 +326,14 @@ struct CgArgs {
                    // partials and commits the scalars, instead of a separate one-thread k_cg_peer_commit_* launch
 };
 
-// the idle direction buffer (see CgArgs::w_out_scr); before_commit: called by the kernel that advances the iteration count
+// buffer `sel` of a preconditioner pass (see CgArgs::w_out_scr); before_commit: called by the kernel that advances the
+// iteration count.  widx: the same choice as an index into PeerTab::wghost_at_*.
 template <typename T>
-__device__ __forceinline__ T *cg_wscratch(const CgArgs<T> &a, int iters, bool before_commit) {
-  return a.pbuf[before_commit ? (iters & 1) : ((iters & 1) ^ 1)];
+__device__ __forceinline__ T *cg_wsel(const CgArgs<T> &a, int sel, int iters, bool before_commit) {
+  return sel == 0 ? a.z : (sel == 2 ? a.y : a.pbuf[before_commit ? (iters & 1) : ((iters & 1) ^ 1)]);
+}
+__device__ __forceinline__ int cg_widx(int sel, int iters, bool before_commit) {
+  return sel == 0 ? PW_Z : (sel == 2 ? PW_Y : (PW_P0 + (before_commit ? (iters & 1) : ((iters & 1) ^ 1))));
 }
 // the buffer holding the current residual (see CgArgs::r2)
 template <typename T>
@@ -499,7 +513,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   STEP_JACOBI  stage r, dinv, p_old : p = dinv.*r + beta*p_old ; writes p, q = M p ; reduces p.q
 //   STEP_Z       stage z, p_old       : p = z + beta*p_old       ; writes p, q = M p ; reduces p.q
 //   STEP_PREC    stage r, dinv        : z0 = dinv.*r ; writes z = pc0*z0 + pc1*dinv.*(M z0) ; reduces r.z
-enum { STEP_JACOBI = 0, STEP_Z = 1, STEP_PREC = 2, STEP_HORNER = 3, STEP_UPDPREC = 4 };   // the last two: cg_step3d.cuh
+enum { STEP_JACOBI = 0, STEP_Z = 1, STEP_PREC = 2, STEP_HORNER = 3, STEP_UPDPREC = 4, STEP_INIT = 5 };   // the last three: cg_step3d.cuh
 
 template <typename T, typename Cfg, int MODE>
 __global__ void __launch_bounds__(Cfg::NT, (Cfg::NT <= 256 ? (MODE != STEP_PREC ? 4 : 3) : 1))
@@ -525,7 +539,7 @@ k_cg_step(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTab 
   const T *__restrict__ p_in = a.pbuf[cur];
   T *__restrict__ p_out = a.pbuf[cur ^ 1];
   const T *__restrict__ rr = (MODE == STEP_Z) ? a.z : cg_rcur(a, it);     // first staged array
-  T *__restrict__ zo = a.w_out_scr ? cg_wscratch(a, it, false) : a.z;     // STEP_PREC output
+  T *__restrict__ zo = cg_wsel(a, a.w_out_scr, it, false);     // STEP_PREC output
   const T *__restrict__ dinv = a.dinv;
   const T rhoM = (T)a.rhoM;
 

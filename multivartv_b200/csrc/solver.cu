@@ -164,8 +164,9 @@ struct mvtv_plan {
   int max_degree = 1;       // highest polynomial degree this plan's kernels implement
   int auto_degree = 1;      // what MVTV_PRECOND_AUTO picks once Jacobi needs more than 24 iterations (measured per family)
   bool fused_update = false;   // one GPU, strip kernels: k_cg_update fused with the first preconditioner pass (r out of place)
-  int tune_fuse3d = 0, tune_horner3d = 0;   // developer knob MVTV_TUNE: tile candidates still being measured
+  int tune_fuse3d = 0, tune_horner3d = 0, tune_init3d = 1;   // developer knob MVTV_TUNE: candidates still being measured
   void *r2 = nullptr;          // second residual buffer of the fused update (allocated on first use)
+  void *ybuf = nullptr;        // third buffer of the Horner passes, degree >= 3 (allocated on first use; with world > 1 at plan creation)
   int zu_variant = -1;   // ZV_* when the compile-time block tables of k_zu_march match this plan, else -1 (gather kernel)
 
   // optional per-kernel-class CUDA-event timing on the plan's stream (mvtv_plan_profile)
@@ -244,7 +245,7 @@ struct mvtv_plan {
     if (cb) cudaFree(cb);
     if (d_peer) cudaFree(d_peer);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pbuf[0], pbuf[1], q, dinv, zbuf, u[0], u[1], S, zr, raw, partials, counters, vid, staging, in_buf, sort_buf, r2};
+    void *bufs[] = {theta, xold, v1, v2, oty, cnt, r, pbuf[0], pbuf[1], q, dinv, zbuf, u[0], u[1], S, zr, raw, partials, counters, vid, staging, in_buf, sort_buf, r2, ybuf};
     for (void *b : bufs)
       if (b) cudaFree(b);
     if (h_scal) cudaFreeHost(h_scal);
@@ -346,35 +347,8 @@ struct mvtv_plan {
       const bool ring = env && std::string(env) == "ring";   // MVTV_STEP=ring: the shared-memory k_cg_step everywhere (cross-checks)
       const bool even = (m[0] % 2 == 0) && m[0] >= 2;
       cg_family = (!ring && even && P == 2) ? CGF_STRIP2D : ((!ring && even && P == 3) ? CGF_STRIP3D : CGF_RING);
-      // Horner passes of degree >= 2 and the fused update exist in the strip kernels, on one GPU (their halo rows need q / w
-      // of the neighbour rank, which the peer protocol does not exchange)
-      const bool strip1 = (cg_family != CGF_RING) && world == 1;
-      max_degree = strip1 ? 4 : 1;
-      auto_degree = strip1 ? 3 : 1;
-      fused_update = strip1;
       const char *efc = getenv("MVTV_FOLD_COMMIT");
       fold_commit = !(efc && std::string(efc) == "0");
-      // MVTV_TUNE="key=value,...": developer knob for A/B measurements of candidates that are still compiled in
-      // (fused=0|1, degree=1..4 for MVTV_PRECOND_AUTO, fuse3d / horner3d = tile candidate)
-      if (const char *tune = getenv("MVTV_TUNE")) {
-        std::string t(tune);
-        size_t pos = 0;
-        while (pos < t.size()) {
-          size_t end = t.find(',', pos);
-          if (end == std::string::npos) end = t.size();
-          const std::string kv = t.substr(pos, end - pos);
-          const size_t eq = kv.find('=');
-          if (eq != std::string::npos) {
-            const std::string k = kv.substr(0, eq);
-            const int v = atoi(kv.c_str() + eq + 1);
-            if (k == "fused") fused_update = fused_update && v != 0;
-            else if (k == "degree") auto_degree = std::max(1, std::min(v, max_degree));
-            else if (k == "fuse3d") tune_fuse3d = v;
-            else if (k == "horner3d") tune_horner3d = v;
-          }
-          pos = end + 1;
-        }
-      }
     }
 
     // 3^P-point stencil of D^T D = sum_b c_b^2 kron_{a in S'_b} L_a  (SURVEY A.6), clamped indices
@@ -473,6 +447,40 @@ struct mvtv_plan {
     MVTV_CUDA(cudaStreamSynchronize(stream));
   }
 
+  // Which preconditioner degrees and which update kernel this plan runs; called once the collectives are known.
+  // Horner passes of degree >= 2 and the fused update exist in the strip kernels: on one GPU, and on several GPUs for 3-D
+  // meshes over the peer-memory path with folded commits (their halo rows need q / w of the neighbour rank, which only
+  // k_cg_step3d exchanges).
+  void finalize_selection() {
+    const bool multi3 = world > 1 && cg_family == CGF_STRIP3D && d_peer && fold_commit;
+    const bool full = (cg_family != CGF_RING) && (world == 1 || multi3);
+    max_degree = full ? 4 : 1;
+    auto_degree = full ? 3 : 1;
+    fused_update = full;
+    // MVTV_TUNE="key=value,...": developer knob for A/B measurements of candidates that are still compiled in
+    // (fused=0|1, degree=1..4 for MVTV_PRECOND_AUTO, fuse3d / horner3d = tile candidate)
+    if (const char *tune = getenv("MVTV_TUNE")) {
+      std::string t(tune);
+      size_t pos = 0;
+      while (pos < t.size()) {
+        size_t end = t.find(',', pos);
+        if (end == std::string::npos) end = t.size();
+        const std::string kv = t.substr(pos, end - pos);
+        const size_t eq = kv.find('=');
+        if (eq != std::string::npos) {
+          const std::string k = kv.substr(0, eq);
+          const int v = atoi(kv.c_str() + eq + 1);
+          if (k == "fused") fused_update = fused_update && v != 0;
+          else if (k == "degree") auto_degree = std::max(1, std::min(v, max_degree));
+          else if (k == "fuse3d") tune_fuse3d = v;
+          else if (k == "horner3d") tune_horner3d = v;
+          else if (k == "init3d") tune_init3d = v;
+        }
+        pos = end + 1;
+      }
+    }
+  }
+
   dim3 grid_owned() const { return dim3(grid.x, (unsigned)dt.nz, 1); }
   static int grid1d(long long n) {
     long long g = (n + 255) / 256;
@@ -509,11 +517,20 @@ struct mvtv_plan {
     const size_t cb_bytes = 8 * (n_slots + n_flags + 4 + 1);
     MVTV_CUDA(cudaMalloc(&cb, cb_bytes));
     MVTV_CUDA(cudaMemset(cb, 0, cb_bytes));
-    struct Handles { cudaIpcMemHandle_t cb, r, z; };
-    static_assert(sizeof(Handles) == 192, "three 64-byte IPC handles");
+    // the 3-D strip kernels also exchange q and the buffers of the Horner passes (z, the two direction buffers, y)
+    const size_t vbytes = (size_t)dt.usz * esz();
+    if (cg_family == CGF_STRIP3D && !ybuf) {
+      MVTV_CUDA(cudaMalloc(&ybuf, vbytes));
+      MVTV_CUDA(cudaMemset(ybuf, 0, vbytes));
+    }
+    struct Handles { cudaIpcMemHandle_t cb, r, z, q, p0, p1, y; };
+    static_assert(sizeof(Handles) == 448, "seven 64-byte IPC handles");
     Handles mine;
+    memset(&mine, 0, sizeof(mine));
     bool ok = cudaIpcGetMemHandle(&mine.cb, cb) == cudaSuccess && cudaIpcGetMemHandle(&mine.r, r) == cudaSuccess &&
-              cudaIpcGetMemHandle(&mine.z, zbuf) == cudaSuccess;
+              cudaIpcGetMemHandle(&mine.z, zbuf) == cudaSuccess && cudaIpcGetMemHandle(&mine.q, q) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.p0, pbuf[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.p1, pbuf[1]) == cudaSuccess &&
+              (!ybuf || cudaIpcGetMemHandle(&mine.y, ybuf) == cudaSuccess);
     // all ranks must take the same decision: all-reduce the ok flag with the handles' exchange
     unsigned char *d_h = nullptr;
     MVTV_CUDA(cudaMalloc(&d_h, sizeof(Handles) * world + 8));
@@ -523,7 +540,8 @@ struct mvtv_plan {
     MVTV_CUDA(cudaStreamSynchronize(stream));
     MVTV_CUDA(cudaMemcpy(all.data(), d_h, sizeof(Handles) * world, cudaMemcpyDeviceToHost));
     std::vector<unsigned char *> pcb(world, nullptr);
-    unsigned char *r_prev = nullptr, *r_next = nullptr, *z_prev = nullptr, *z_next = nullptr;
+    // neighbours' buffers, in the order r, z, q, p0, p1, y
+    unsigned char *nb_prev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, *nb_next[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int j = 0; ok && j < world; ++j) {
       if (j == rank) { pcb[j] = cb; continue; }
       void *p = nullptr;
@@ -531,14 +549,13 @@ struct mvtv_plan {
       ipc_opened.push_back(p);
       pcb[j] = (unsigned char *)p;
       if (j == rank - 1 || j == rank + 1) {
-        void *pr = nullptr;
-        if (cudaIpcOpenMemHandle(&pr, all[j].r, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
-        ipc_opened.push_back(pr);
-        (j == rank - 1 ? r_prev : r_next) = (unsigned char *)pr;
-        void *pz = nullptr;
-        if (cudaIpcOpenMemHandle(&pz, all[j].z, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
-        ipc_opened.push_back(pz);
-        (j == rank - 1 ? z_prev : z_next) = (unsigned char *)pz;
+        const cudaIpcMemHandle_t hs[6] = {all[j].r, all[j].z, all[j].q, all[j].p0, all[j].p1, all[j].y};
+        for (int k = 0; ok && k < (ybuf ? 6 : 5); ++k) {
+          void *pb = nullptr;
+          if (cudaIpcOpenMemHandle(&pb, hs[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+          ipc_opened.push_back(pb);
+          (j == rank - 1 ? nb_prev : nb_next)[k] = (unsigned char *)pb;
+        }
       }
     }
     cudaGetLastError();
@@ -570,10 +587,17 @@ struct mvtv_plan {
     // the slab of rank j has its own nz; its ghost-above plane starts at (nz_j + 1) * plane
     const long long mz = dt.m[dt.P - 1], basez = mz / world, extra = mz % world;
     auto nz_of = [&](int j) { return basez + (j < extra ? 1 : 0); };
-    pt.rghost_at_prev = dt.has_lo ? (void *)(r_prev + esz() * (size_t)((nz_of(rank - 1) + 1) * dt.plane)) : nullptr;
-    pt.rghost_at_next = dt.has_hi ? (void *)r_next : nullptr;
-    pt.zghost_at_prev = dt.has_lo ? (void *)(z_prev + esz() * (size_t)((nz_of(rank - 1) + 1) * dt.plane)) : nullptr;
-    pt.zghost_at_next = dt.has_hi ? (void *)z_next : nullptr;
+    // rank j-1's ghost plane ABOVE its slab starts at (nz_{j-1} + 1) * plane; rank j+1's ghost plane BELOW is its plane 0
+    auto at_prev = [&](int k) { return (dt.has_lo && nb_prev[k]) ? (void *)(nb_prev[k] + esz() * (size_t)((nz_of(rank - 1) + 1) * dt.plane)) : nullptr; };
+    auto at_next = [&](int k) { return (dt.has_hi && nb_next[k]) ? (void *)nb_next[k] : nullptr; };
+    pt.rghost_at_prev = at_prev(0);
+    pt.rghost_at_next = at_next(0);
+    pt.zghost_at_prev = at_prev(1);
+    pt.zghost_at_next = at_next(1);
+    pt.qghost_at_prev = at_prev(2);
+    pt.qghost_at_next = at_next(2);
+    const int wk[4] = {1, 3, 4, 5};   // PW_Z, PW_P0, PW_P1, PW_Y
+    for (int w = 0; w < 4; ++w) { pt.wghost_at_prev[w] = at_prev(wk[w]); pt.wghost_at_next[w] = at_next(wk[w]); }
     pt.zflag_from_prev = hflags_of(cb) + 2;
     pt.zflag_from_next = hflags_of(cb) + 3;
     pt.zflag_at_prev = dt.has_lo ? hflags_of(pcb[rank - 1]) + 3 : nullptr;
@@ -872,6 +896,10 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     MVTV_CUDA(cudaMalloc(&r2, (size_t)dt.usz * esz()));
     MVTV_CUDA(cudaMemsetAsync(r2, 0, (size_t)dt.usz * esz(), stream));
   }
+  if (deg >= 3 && !ybuf) {   // world > 1: allocated (and shared with the neighbours) at plan creation
+    MVTV_CUDA(cudaMalloc(&ybuf, (size_t)dt.usz * esz()));
+    MVTV_CUDA(cudaMemsetAsync(ybuf, 0, (size_t)dt.usz * esz(), stream));
+  }
   CgArgs<T> a;
   a.x = (T *)theta;
   a.xold = (T *)xold;
@@ -894,7 +922,15 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   a.seq_halo = 0;
   a.seq_zhalo = 0;
   a.z = (T *)zbuf;
+  a.y = (T *)ybuf;
   a.prec = deg;
+  // buffer a preconditioner pass writes (0 = z, 1 = idle direction buffer, 2 = y): no buffer is rewritten before the pass
+  // after next, the last pass writes z
+  auto wsel = [deg](int j) {
+    static const int rot[5][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {1, 0, 0, 0}, {1, 2, 0, 0}, {0, 1, 2, 0}};
+    return rot[deg][j - 1];
+  };
+  unsigned long long z_event = 0;   // z-flag event of the latest exported planes (several GPUs)
   // coefficients c_0 .. c_d of the degree-d polynomial P in D^-1 M whose residual 1 - t P(t) is the Chebyshev polynomial
   // T_{d+1} on [bmax/kappa, bmax]; Horner form: w_1 = c_d A z0 + c_{d-1} z0, w_k = A w_{k-1} + c_{d-k} z0, z = w_d
   double hc[8] = {0};
@@ -972,6 +1008,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
         sh.occ[K_STEP_J] = occ_of(k_cg_step3d<T, S3Step, STEP_JACOBI>, S3Step::NT, 0);
         sh.occ[K_STEP_Z] = occ_of(k_cg_step3d<T, S3Step, STEP_Z>, S3Step::NT, 0);
         sh.occ[K_PREC] = occ_of(k_cg_step3d<T, S3Prec, STEP_PREC>, S3Prec::NT, 0);
+        sh.occ[K_INIT] = occ_of(k_cg_step3d<T, S3Prec, STEP_INIT>, S3Prec::NT, 0);
         sel3(tune_horner3d, [&](auto k) { using C3 = typename S3HornerSel<decltype(k)::value>::Cfg; sh.occ[K_HORNER] = occ_of(k_cg_step3d<T, C3, STEP_HORNER>, C3::NT, 0); });
         sel3(tune_fuse3d, [&](auto k) { using C3 = typename S3FuseSel<decltype(k)::value>::Cfg; sh.occ[K_FUSED] = occ_of(k_cg_step3d<T, C3, STEP_UPDPREC>, C3::NT, 0); });
       }
@@ -1016,6 +1053,14 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       init_done = true;
     }
   }
+  if constexpr (HAS3D) {
+    if (fam == CGF_STRIP3D && tune_init3d) {   // marching / shuffle form (STEP_INIT of cg_step3d.cuh)
+      int zc_init = 1;
+      const dim3 gi = chunking(tiles_prec, sh.occ[K_INIT], zc_init);
+      k_cg_step3d<T, S3Prec, STEP_INIT><<<gi, S3Prec::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1}, zc_init);
+      init_done = true;
+    }
+  }
   if (!init_done) k_cg_init<T, P><<<g, block, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1});
   prof_end();
   MVTV_CUDA(cudaGetLastError());
@@ -1033,8 +1078,9 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   // ---- the launches of one CG iteration
   // first preconditioner pass, stand-alone (before the first iteration on the fused path, every iteration otherwise)
   auto launch_prec_first = [&]() {
-    a.w_out_scr = (deg >= 2 && ((deg - 1) % 2 == 1)) ? 1 : 0;   // pass j writes z when deg - j is even
+    a.w_out_scr = wsel(1);
     a.w_in_scr = 0;
+    a.seq_zout = a.seq_zhalo = z_event = ++zhalo_seq;
     a.final_pass = (deg == 1) ? 1 : 0;
     a.pc0 = hc[deg - 1];
     a.pc1 = hc[deg];
@@ -1059,8 +1105,11 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   // Horner passes 2 .. deg (strip kernels, one GPU)
   auto launch_horner_rest = [&]() {
     for (int j = 2; j <= deg; ++j) {
-      a.w_out_scr = ((deg - j) % 2 == 1) ? 1 : 0;
-      a.w_in_scr = ((deg - j + 1) % 2 == 1) ? 1 : 0;
+      a.w_out_scr = wsel(j);
+      a.w_in_scr = wsel(j - 1);
+      a.seq_zin = z_event;
+      a.seq_zout = z_event = ++zhalo_seq;
+      if (j == deg) a.seq_red = ++red_seq;
       a.final_pass = (j == deg) ? 1 : 0;
       a.pc0 = hc[deg - j];
       a.pc1 = 0.0;
@@ -1093,6 +1142,8 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   };
   auto launch_step = [&]() {   // p = z + beta p (Jacobi: z = D^-1 r on the fly), q = M p, p.q
     const RedBuf rbs{partials, counters + 2};
+    a.seq_zin = z_event;                                        // ghost planes of z
+    if (fused && d_peer) a.seq_zout = z_event = ++zhalo_seq;    // ... and this launch exports those of q
     bool done = false;
     if constexpr (HAS2D) {
       if (fam == CGF_STRIP2D) {
@@ -1126,8 +1177,10 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   auto launch_update = [&]() {   // theta += alpha p, r -= alpha q, r.r (Jacobi: r.z too); fused: + first preconditioner pass
     const RedBuf rbu{partials, counters + 3};
     if (fused) {
-      a.w_out_scr = (deg >= 2 && ((deg - 1) % 2 == 1)) ? 1 : 0;
+      a.w_out_scr = wsel(1);
       a.w_in_scr = 0;
+      a.seq_zin = z_event;                        // ghost planes of q
+      a.seq_zout = z_event = ++zhalo_seq;
       a.final_pass = (deg == 1) ? 1 : 0;
       a.pc0 = hc[deg - 1];
       a.pc1 = hc[deg];
@@ -1168,8 +1221,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       if (world > 1 && !d_peer) exchange_ghosts<T>((T *)r);
       if (deg && !(fused && first_prec_done)) {  // z = P(D^-1 M) D^-1 r and r.z (fused path: only before the first iteration)
         first_prec_done = true;
-        a.seq_red = ++red_seq;
-        a.seq_zhalo = ++zhalo_seq;
+        a.seq_red = ++red_seq;       // of the pass that reduces r.z (the last one)
         prof_begin(MVTV_KC_CG_PREC);
         launch_prec_first();
         launch_horner_rest();
@@ -1181,7 +1233,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       launch_step();
       prof_end();
       a.seq_red = ++red_seq;
-      a.seq_halo = ++halo_seq;
+      if (!fused) a.seq_halo = ++halo_seq;   // k_cg_update posts r's ghost planes; the fused update keeps them up to date locally
       prof_begin(MVTV_KC_CG_UPDATE);
       launch_update();
       prof_end();
@@ -1581,6 +1633,7 @@ int mvtv_plan_create(mvtv_plan **out, const mvtv_plan_desc *d) {
       MVTV_NCCL(g_nccl.CommInitRank(&pl->comm, d->world, id, d->rank));
       pl->setup_peer();
     }
+    pl->finalize_selection();
     *out = pl.release();
     return MVTV_OK;
   });

@@ -472,10 +472,13 @@ def kfoldinds(n, k, seed=117):
 
 
 def mbs(data, y, m, mesh=None, n_lambda=100, ftrue=None, lambdas=None, folds=5, verbose=False, mode="rcpp",
-        foldinds=None, seed=117, dtype=F64, variant=VARIANT_REFERENCE, **solve_kw):
+        foldinds=None, seed=117, dtype=F64, variant=VARIANT_REFERENCE, devices=None, **solve_kw):
     """Cross-validated fit over a path of lambdas: ``mbs`` / ``mbs_impl`` (cpp-code/solvers.cpp:277-310,
     rcpp-code/MultivarTV/src/solvers.cpp:305-376).  Follows the rcpp semantics (per-fold operators, fresh path per
     fold; SURVEY section 3 lists the cpp-code CV bugs).  ``mode`` selects the ADMM loop ("cpp" / "rcpp").
+    ``devices``: CUDA ordinals for the cross-validation folds -- the folds are independent solves (cpp-code/solvers.cpp:300-304,
+    rcpp solvers.cpp:341-352), so each runs as its own plan, one host thread per plan, round-robin over the listed GPUs
+    (replica-level parallelism: no collective on the data path); None = one after the other on the current device.
     Returns the rcpp list as a dict plus the Python prototype's keys (code/solvers.py:140)."""
     data = np.asarray(data, dtype=np.float64)
     if data.ndim == 1:
@@ -517,15 +520,31 @@ def mbs(data, y, m, mesh=None, n_lambda=100, ftrue=None, lambdas=None, folds=5, 
             if foldinds is None:
                 foldinds = kfoldinds(n, folds, seed)
             foldinds = np.asarray(foldinds)
-            for f in range(folds):
+
+            def run_fold(f, pl):
                 tr, te = foldinds != f, foldinds == f
-                plan.set_points(data[tr], y[tr], axes)          # per-fold operators (rcpp :347-348)
-                path = plan.solve_path(LAMBDAS, y[tr], mode=mode, want_thetas=True, want_best=False, **solve_kw)
+                pl.set_points(data[tr], y[tr], axes)            # per-fold operators (rcpp :347-348)
+                path = pl.solve_path(LAMBDAS, y[tr], mode=mode, want_thetas=True, want_best=False, **solve_kw)
                 idx_te = nearest1(data[te], axes=axes)
                 for i in range(nl):                             # test_mse (rcpp :278-288)
                     mse_mat[i, f] = float(np.sum((path["thetas"][i][idx_te] - y[te]) ** 2) / te.sum())
                 if verbose:
                     print("Fold Complete: %d" % f)
+
+            if devices:
+                from concurrent.futures import ThreadPoolExecutor
+                devs = [int(d) for d in devices]
+
+                def worker(k):                                  # one plan per host thread, folds k, k + len(devs), ...
+                    with Plan(m, deltas=deltas, dtype=dtype, variant=variant, device=devs[k]) as pl:
+                        for f in range(k, folds, len(devs)):
+                            run_fold(f, pl)
+                with ThreadPoolExecutor(max_workers=len(devs)) as ex:
+                    for fut in [ex.submit(worker, k) for k in range(min(len(devs), folds))]:
+                        fut.result()
+            else:
+                for f in range(folds):
+                    run_fold(f, plan)
             plan.set_points(data, y, axes)                      # final path on the full data (rcpp :355-358)
             final = plan.solve_path(LAMBDAS, y, mode=mode, want_thetas=True, **solve_kw)
             idx_all = plan.cache()[2]

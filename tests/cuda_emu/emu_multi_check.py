@@ -60,8 +60,15 @@ def main():
         cases += [([12, 12, 12], 1500, "rcpp", 0.7, 3, C1, 2, comm), ([66, 4, 9], 2000, "rcpp", 1.0, 2, C1, 2, comm),
                   ([8, 8, 8], 600, "rcpp", 0.7, 3, J, 3, comm), ([12, 12, 12], 1500, "rcpp", 0.7, 3, C1, 2, comm, {"MVTV_STEP": "ring"}),
                   ([24, 22], 3000, "rcpp", 1.0, 4, mv.PRECOND_CHEB3, 3, comm), ([24, 22], 3000, "rcpp", 1.0, 4, mv.PRECOND_AUTO, 2, comm)]
+    # 3-D strip kernels over the peer path with folded commits: fused update (q exchanged, r kept up to date on the ghost planes)
+    # and Horner passes of degree 2..4 (pass outputs rotate over z / idle direction buffer / y, one flag event per exchange)
+    cases += [([12, 12, 12], 1500, "rcpp", 0.7, 4, mv.PRECOND_CHEB3, 2, "fold"), ([8, 8, 9], 2000, "rcpp", 0.7, 5, mv.PRECOND_CHEB2, 3, "fold"),
+              ([8, 8, 10], 2000, "rcpp", 0.7, 4, mv.PRECOND_CHEB4, 4, "fold"), ([12, 12, 12], 1500, "rcpp", 0.7, 6, mv.PRECOND_AUTO, 3, "fold"),
+              ([66, 4, 9], 2000, "rcpp", 1.0, 3, mv.PRECOND_CHEB3, 2, "fold"), ([12, 12, 12], 1500, "cpp", 2.0, 0, mv.PRECOND_CHEB4, 2, "fold")]
     if quick:
-        cases = [cases[0], cases[3], cases[4], cases[9]]
+        cases = [cases[0], cases[3], cases[4], cases[9], cases[-6], cases[-4]]
+    if len(sys.argv) > 2 and sys.argv[2] == "last":
+        cases = cases[-6:]
     fail = 0
     for case in cases:
         dims, n, mode, lam, max_passes, precond, world, comm = case[:8]

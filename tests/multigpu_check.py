@@ -34,7 +34,11 @@ def main():
              ([8, 8, 8, 9], 5000, "rcpp", 1.0, 25, J), ([64, 64], 20000, "py", 0.8, 0, J),
              ([40, 40, 40], 64000, "rcpp", 1.0, 15, J), ([24, 22], 3000, "rcpp", 1.0, 0, C1),
              ([12, 12, 13], 4000, "rcpp", 0.7, 0, C1), ([8, 8, 8, 9], 5000, "rcpp", 1.0, 25, C1),
-             ([40, 40, 40], 64000, "rcpp", 1.0, 15, C1)]
+             ([40, 40, 40], 64000, "rcpp", 1.0, 15, C1),
+             # 3-D strip kernels on the peer path: fused update + Horner passes of degree 2..4, and what AUTO picks
+             ([40, 40, 40], 64000, "rcpp", 1.0, 15, mv.PRECOND_CHEB2), ([40, 40, 40], 64000, "rcpp", 1.0, 15, mv.PRECOND_CHEB3),
+             ([40, 40, 40], 64000, "rcpp", 1.0, 15, mv.PRECOND_CHEB4), ([40, 40, 40], 64000, "rcpp", 1.0, 15, mv.PRECOND_AUTO),
+             ([66, 12, 24], 30000, "rcpp", 0.7, 10, mv.PRECOND_AUTO), ([24, 24, 24], 20000, "cpp", 2.0, 0, mv.PRECOND_CHEB3)]
     if os.environ.get("MVTV_MG_ONLY2D"):   # short run: the 2-D cases only (k_cg_step2d's ghost-row / peer-memory protocol)
         cases = [c for c in cases if len(c[0]) == 2 and c[2] != "py"] + [([64, 64], 20000, "rcpp", 0.8, 40, C1)]
     for dims, n, mode, lam, max_passes, precond in cases:
@@ -47,7 +51,8 @@ def main():
         xo, yo = partition.exchange_points(xs, ys, axes[-1])
         box = [mv.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        with mv.Plan(dims, device=local, rank=rank, world=world, nccl_unique_id=box[0]) as pl:
+        variant = mv.VARIANT_REFERENCE if (p < 3 or dims[0] == dims[1]) else mv.VARIANT_INTENDED   # reference operator: cpp-code/utils.cpp:187
+        with mv.Plan(dims, variant=variant, device=local, rank=rank, world=world, nccl_unique_id=box[0]) as pl:
             pl.set_points(xo, yo, axes)
             out = pl.solve(lam, mode=mode, max_passes=max_passes, want_fitted=False, cg_rtol=1e-13, precond=precond)
             gathered = [None] * world
@@ -56,7 +61,7 @@ def main():
             gathered.sort(key=lambda t: t[0])
             theta = np.concatenate([g[1] for g in gathered])
             big = int(np.prod(dims)) > 20000
-            ref = co.mbs_one(x, y, dims, axes, lam, mode=imode, max_passes=max_passes,
+            ref = co.mbs_one(x, y, dims, axes, lam, mode=imode, max_passes=max_passes, variant=variant,
                              solver=co.SOLVER_PCG if big else co.SOLVER_BANDCHOL, cg_rtol=1e-13)
             err = float(np.abs(theta - ref["theta"]).max())
             same = all(g[2] == ref["counter"] for g in gathered)

@@ -104,11 +104,13 @@ def test_host_mesh_helpers_match_reference_semantics():
 
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver times beside ours) prints one JSON line with the contract's
-    keys; it runs the oracle port on the bounded 1024^2 sample, no GPU involved."""
+    keys; it runs the oracle port on the bounded 128^3 sample of the default workload with ALL host threads -- also under
+    torchrun's OMP_NUM_THREADS=1 -- and says in `config` which mesh it really timed; ranks other than 0 print nothing."""
     import json
     import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -119,4 +121,9 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["metric"] == "mesh_vertex_updates_per_sec" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
-    assert d["vs_baseline"] is None and d["config"]["workload"].startswith("2-D 4096x4096")
+    assert d["vs_baseline"] is None and d["config"]["mesh"] == [128, 128, 128] and d["config"]["same_config"] is False
+    assert d["config"]["sample_of"]["mesh"] == [512, 512, 512] and d["sample_vertices"] == 128 ** 3
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""

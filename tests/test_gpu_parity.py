@@ -437,6 +437,12 @@ def test_mbs_cv_driver(mv):
     assert np.abs(out["fitted"] - final[best]["fitted"]).max() <= FP64_TOL
     assert [mm["lambda"] for mm in out["models"]] == list(lambdas)
     assert np.allclose(out["residuals"], y - out["fitted"])
+    # the folds as replicas: one plan per host thread, round-robin over the box's GPUs (two threads on one GPU when it has one)
+    import ctypes as C
+    ndev = C.c_int(0)
+    mv._lib.load().mvtv_device_count(C.byref(ndev))
+    rep = mv.mbs(x, y, m, lambdas=lambdas, folds=folds, mode="rcpp", foldinds=foldinds, devices=[0, 1 % max(1, ndev.value)])
+    assert np.allclose(rep["cv.mse_mat"], mse_mat, rtol=1e-9, atol=1e-11) and np.abs(rep["theta_hat"] - out["theta_hat"]).max() <= 1e-10
     # folds = 1 with the default grid: runs end to end, picks the smallest training MSE
     out1 = mv.mbs(x, y, m, n_lambda=6, folds=1, mode="rcpp")
     assert len(out1["models"]) == 6 and out1["lambda_minmse_ind"] == int(np.argmin(out1["cv.mses"])) + 1
