@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MVTV_ABI_VERSION 1
+#define MVTV_ABI_VERSION 2
 #define MVTV_MAXP 4
 
 /* status codes */
@@ -100,7 +100,8 @@ typedef struct {
   int32_t cg_maxit;     /* 0 -> 20000 (f64) / 1000 (f32; reaching it is not an error in f32) */
   int32_t precond;      /* MVTV_PRECOND_* */
   uint32_t flags;       /* MVTV_WARM_* */
-  int32_t reserved;
+  int32_t timing_skip_passes; /* benchmarking: device_seconds and the timed_* results start after this many ADMM passes (the
+                           warm-up passes run inside the same call, so no pass is special); 0 = time the whole loop */
 } mvtv_solve_params;
 
 typedef struct {
@@ -113,8 +114,12 @@ typedef struct {
   double s_norm;        /* last ||dual_residual||_2 */
   double max_dtheta;    /* last max|theta - thetaold| (the CPP/PY loop test, cpp-code/solvers.cpp:113) */
   int64_t inner_iters;  /* CG iterations summed over all passes */
-  double device_seconds;/* CUDA-event time of the ADMM loop on the plan's stream */
+  double device_seconds;/* CUDA-event time of the ADMM loop on the plan's stream (after timing_skip_passes passes) */
   int64_t kernel_launches; /* kernels of this library launched by this call */
+  int64_t timed_inner_iters;     /* CG iterations, ADMM passes and kernel launches inside the device_seconds interval */
+  int64_t timed_kernel_launches;
+  int32_t timed_passes;
+  int32_t reserved2;
 } mvtv_solve_result;
 
 /* -- library ------------------------------------------------------------------------------------ */

@@ -40,13 +40,15 @@ class SolveParams(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("mode", C.c_int32), ("lam", C.c_double),
                 ("rho_init", C.c_double), ("rho_matrix0", C.c_double), ("tol", C.c_double),
                 ("max_counter", C.c_int32), ("max_passes", C.c_int32), ("cg_rtol", C.c_double),
-                ("cg_maxit", C.c_int32), ("precond", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_int32)]
+                ("cg_maxit", C.c_int32), ("precond", C.c_int32), ("flags", C.c_uint32), ("timing_skip_passes", C.c_int32)]
 
 
 class SolveResult(C.Structure):
     _fields_ = [("counter", C.c_int32), ("passes", C.c_int32), ("status", C.c_int32), ("reserved", C.c_int32),
                 ("rho", C.c_double), ("r_norm", C.c_double), ("s_norm", C.c_double), ("max_dtheta", C.c_double),
-                ("inner_iters", C.c_int64), ("device_seconds", C.c_double), ("kernel_launches", C.c_int64)]
+                ("inner_iters", C.c_int64), ("device_seconds", C.c_double), ("kernel_launches", C.c_int64),
+                ("timed_inner_iters", C.c_int64), ("timed_kernel_launches", C.c_int64), ("timed_passes", C.c_int32),
+                ("reserved2", C.c_int32)]
 
 
 class MvtvError(RuntimeError):

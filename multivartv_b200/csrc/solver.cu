@@ -149,6 +149,8 @@ struct mvtv_plan {
   long long launches = 0;
   int last_cg_iters = 8;
   int last_cg_prec = 0;     // polynomial degree of the previous x-update (0 = Jacobi)
+  double jac_estimate = 100.0; // MVTV_PRECOND_AUTO: decaying maximum of the Jacobi-equivalent iteration counts (a cold start is
+                               // assumed hard: the first x-update from theta = mean(y) is the longest of a solve)
   // peer-memory collectives of the CG loop (CUDA IPC); falls back to NCCL when unavailable or MVTV_COMM=nccl
   unsigned char *cb = nullptr;          // this rank's comm buffer (slots, flags, halo flags, error word)
   PeerTab *d_peer = nullptr;            // device copy of the peer table, nullptr = NCCL path
@@ -656,6 +658,9 @@ struct mvtv_plan {
     n = npts;
     have_points = true;
     have_u_state = have_theta_state = false;
+    jac_estimate = 100.0;   // new operators: MVTV_PRECOND_AUTO starts over (results then depend on the data only, not on
+    last_cg_iters = 8;      // what the plan solved before)
+    last_cg_prec = 0;
   }
   double sum_y(const double *y_dev, long long npts, double flag);
 
@@ -1430,10 +1435,17 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
     dmax = h_scal[0];
   }
 
-  MVTV_CUDA(cudaEventRecord(ev0, stream));
+  const int skip = prm.timing_skip_passes > 0 ? prm.timing_skip_passes : 0;   // untimed warm-up passes of a benchmark call
+  long long launches_t0 = launches, inner_t0 = 0;
+  int passes_t0 = 0;
+  if (skip == 0) MVTV_CUDA(cudaEventRecord(ev0, stream));
   // alpha = D*theta (cpp :100): only D^T alpha and D^T u are needed, computed by the init pass
   launch_zu<T>(0.0, uscale, mode, 1, false);
+  // scale still to be applied to the stored D^T u when b is formed: the initial pass above has folded a pending rescale of a
+  // warm-started u into it; after a regular pass D^T u_new is stored unscaled and adapt_step's factor is pending
+  double v2scale = 1.0;
 
+  const bool trace_passes = getenv("MVTV_TRACE") != nullptr && rank == 0;
   int counter = 1, passes = 0, status = MVTV_OK;
   double dual_norm = 1.0, primal_norm = 1.0, eps_dual = tol, eps_primal = tol;  // rcpp :108-109
   double r_norm = NAN, s_norm = NAN;
@@ -1446,11 +1458,21 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
       if (!(dmax > tol)) break;  // cpp :113 any(abs(theta-thetaold) > TOL)
     }
     if (prm.max_passes > 0 && passes >= prm.max_passes) break;
+    if (skip > 0 && passes == skip) {
+      MVTV_CUDA(cudaEventRecord(ev0, stream));
+      launches_t0 = launches;
+      inner_t0 = inner;
+      passes_t0 = passes;
+    }
     // b = Oty + rho*Dt*(alpha+u) ; theta = spsolve(sp_crosses, b)     cpp :115-116 / rcpp :112-113
     int cgst = MVTV_OK;
     // AUTO: the polynomial pays off once plain Jacobi-PCG needs more than ~24 iterations (degree d needs ~0.86 (d+1) times
-    // fewer iterations for d more stencil passes); the estimate comes from the previous x-update on this plan
-    const double jac_equiv = last_cg_prec ? 0.86 * (last_cg_prec + 1) * last_cg_iters : (double)last_cg_iters;
+    // fewer iterations for d more stencil passes).  The estimate is the Jacobi-equivalent count of the previous x-updates on
+    // this plan with a memory of one half per pass, so that one easy solve (e.g. the first pass of a warm-started call)
+    // does not send the next, ordinary one back to Jacobi
+    const double jac_last = last_cg_prec ? 0.86 * (last_cg_prec + 1) * last_cg_iters : (double)last_cg_iters;
+    jac_estimate = std::max(jac_last, 0.5 * jac_estimate);
+    const double jac_equiv = jac_estimate;
     int prec;
     switch (prm.precond) {
       case MVTV_PRECOND_JACOBI: prec = 0; break;
@@ -1463,11 +1485,14 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
     prec = std::min(prec, max_degree);
     last_cg_prec = prec;
     switch (dt.P) {
-      case 2: cg_solve<T, 2>(rho, uscale, rhoM, cg_rtol, cg_maxit, prec, inner, cgst); break;
-      case 3: cg_solve<T, 3>(rho, uscale, rhoM, cg_rtol, cg_maxit, prec, inner, cgst); break;
-      case 4: cg_solve<T, 4>(rho, uscale, rhoM, cg_rtol, cg_maxit, prec, inner, cgst); break;
+      case 2: cg_solve<T, 2>(rho, v2scale, rhoM, cg_rtol, cg_maxit, prec, inner, cgst); break;
+      case 3: cg_solve<T, 3>(rho, v2scale, rhoM, cg_rtol, cg_maxit, prec, inner, cgst); break;
+      case 4: cg_solve<T, 4>(rho, v2scale, rhoM, cg_rtol, cg_maxit, prec, inner, cgst); break;
       default: throw Error(MVTV_ERR_UNSUPPORTED, "p must be 1..4");
     }
+    if (trace_passes)
+      fprintf(stderr, "[mvtv] pass %d: rho %.6g matrix scalar %.6g degree %d, %d CG iterations (status %d)\n", passes + 1, rho, rhoM, prec,
+              last_cg_iters - 1, cgst);
     if (cgst != MVTV_OK) { status = cgst; break; }
     exchange_ghosts<T>(th);
     // alpha, residuals, u update: cpp :117-120 / rcpp :114-117
@@ -1480,6 +1505,7 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
     s_norm = fabs(rho) * sqrt(h_scal[ZR_S2]);
     dmax = h_scal[ZR_DMAX];
     ++passes;
+    v2scale = uscale;
     if (mode == MVTV_MODE_PY) continue;  // no residuals, no adaptation; counter never moves (py :65-76)
     if (mode == MVTV_MODE_CPP) {
       counter += 1;
@@ -1499,12 +1525,13 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
       counter += 1;
       if (counter > max_counter) { status = MVTV_ERR_NOT_CONVERGED; break; }    // rcpp :129-132
     }
+    v2scale = uscale;
   }
   MVTV_CUDA(cudaEventRecord(ev1, stream));
   MVTV_CUDA(cudaStreamSynchronize(stream));
   prof_flush();
   float ms = 0.f;
-  MVTV_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  if (skip == 0 || passes > skip) MVTV_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   have_theta_state = true;
   have_u_state = true;
   rho_state = rho;
@@ -1542,6 +1569,9 @@ int mvtv_plan::solve_t(const mvtv_solve_params &prm, const double *theta_init, d
   res.inner_iters = inner;
   res.device_seconds = (double)ms * 1e-3;
   res.kernel_launches = launches - launches0;
+  res.timed_passes = passes - passes_t0;
+  res.timed_inner_iters = inner - inner_t0;
+  res.timed_kernel_launches = launches - launches_t0;
   return status;
 }
 

@@ -267,7 +267,7 @@ class Plan:
     def solve(self, lam, mode="cpp", theta_init=None, u_init=None, rho_init=None, rho_matrix0=None, tol=None,
               max_counter=0, max_passes=0, cg_rtol=0.0, cg_maxit=0, precond=PRECOND_AUTO, flags=0,
               want_u=False, want_fitted=True, want_theta=True, raise_on_nonconvergence=True, theta_out=None,
-              fitted_out=None):
+              fitted_out=None, timing_skip_passes=0):
         """admm_update + fitted (mvtv_solve).  ``theta_out`` / ``fitted_out``: optional preallocated float64 arrays
         (``pinned_empty``) that receive the outputs instead of fresh numpy arrays."""
         L = _lib.load()
@@ -280,6 +280,7 @@ class Plan:
         prm.tol = math.nan if tol is None else float(tol)
         prm.max_counter, prm.max_passes = int(max_counter), int(max_passes)
         prm.cg_rtol, prm.cg_maxit, prm.precond, prm.flags = float(cg_rtol), int(cg_maxit), int(precond), int(flags)
+        prm.timing_skip_passes = int(timing_skip_passes)
         th0 = None if theta_init is None else _f64(np.asarray(theta_init).ravel())
         if th0 is not None:
             assert th0.size == self.n_local
@@ -305,7 +306,8 @@ class Plan:
         return dict(theta=theta, fitted=fitted, u=u, rho=res.rho, counter=res.counter, passes=res.passes,
                     status=res.status, r_norm=res.r_norm, s_norm=res.s_norm, max_dtheta=res.max_dtheta,
                     inner_iters=int(res.inner_iters), device_seconds=res.device_seconds,
-                    kernel_launches=int(res.kernel_launches))
+                    kernel_launches=int(res.kernel_launches), timed_passes=int(res.timed_passes),
+                    timed_inner_iters=int(res.timed_inner_iters), timed_kernel_launches=int(res.timed_kernel_launches))
 
     def solve_path(self, lambdas, ftrue, mode="cpp", tol=None, max_counter=0, cg_rtol=0.0, cg_maxit=0,
                    rho_init=None, want_thetas=False, want_best=True, precond=PRECOND_AUTO):

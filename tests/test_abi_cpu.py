@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(lib, name), "libmvtv_b200.so does not export %s" % name
     assert sorted(_lib.SYMBOLS) == declared
-    assert lib.mvtv_abi_version() == 1
+    assert lib.mvtv_abi_version() == 2
 
 
 def test_struct_layouts_match_header(tmp_path):

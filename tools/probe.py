@@ -46,15 +46,11 @@ def main():
             pl.set_points(x, y, axes)
             kw = dict(mode="rcpp", cg_rtol=1e-13 if args.dtype == "f64" else 0.0, want_fitted=False, raise_on_nonconvergence=False,
                       precond=PRE[name])
-            rw = pl.solve(args.lam, max_passes=args.warmup, want_theta=False, **kw)
-            warm = mv.WARM_THETA_FROM_PLAN | mv.WARM_U_FROM_PLAN
-            r = pl.solve(args.lam, max_passes=args.passes, flags=warm, rho_init=rw["rho"], rho_matrix0=rw["rho"], **kw)
-            ms_pass = 1e3 * r["device_seconds"] / max(1, r["passes"])
+            r = pl.solve(args.lam, max_passes=args.warmup + args.passes, timing_skip_passes=args.warmup, **kw)
+            ms_pass = 1e3 * r["device_seconds"] / max(1, r["timed_passes"])
             d = pl.describe()
-            # same passes again with the profiling events on, from the same warm state? no: continue (the per-class
-            # times do not depend on which passes they are)
-            pl.profile(True)
-            rp = pl.solve(args.lam, max_passes=2, flags=warm, rho_init=r["rho"], rho_matrix0=r["rho"], want_theta=False, **kw)
+            pl.profile(True)   # the same call again with the per-class events on (their cost is why it is a second call)
+            rp = pl.solve(args.lam, max_passes=args.warmup + 2, want_theta=False, **kw)
             prof = pl.get_profile()
             pl.profile(False)
         if ref is None:
@@ -68,7 +64,7 @@ def main():
         cls = " ".join("%s=%.1f" % (k, 1e3 * prof[k][0] / perf[k]) for k in ("cg_step", "cg_update", "cg_prec", "zu", "cg_init")
                        if perf.get(k) and prof[k][1])
         print("time %-22s mesh=%s degree=%d fused=%d ms/pass=%.3f inner/pass=%.1f max|dtheta|=%.1e  us/launch-group: %s" % (
-            var, "x".join(map(str, m)), deg, 1 if fused else 0, ms_pass, r["inner_iters"] / max(1, r["passes"]), err, cls), flush=True)
+            var, "x".join(map(str, m)), deg, 1 if fused else 0, ms_pass, r["timed_inner_iters"] / max(1, r["timed_passes"]), err, cls), flush=True)
 
 
 if __name__ == "__main__":
