@@ -21,10 +21,21 @@
 
 namespace mvtv {
 
-template <int WARPS_, int RY_, int MINB_ = 0, bool NOC_ = true>
+// TMAD_: 0 = the rows of a plane are loaded straight into registers, one plane ahead of their use; >= 2 = TMA staging: lanes
+// issue one bulk copy (cp.async.bulk, 512 bytes) per row and array into a per-warp ring of TMAD_ stages in shared memory,
+// TMAD_ - 1 planes ahead, tracked by one mbarrier per stage.  The ring is private to the warp (its own lanes are the only
+// readers, so a stage is free again as soon as the warp has passed it: no empty-barrier, no CTA barrier in the loop); the
+// halo rows it duplicates with the neighbouring warps come out of L2.
+template <int WARPS_, int RY_, int MINB_ = 0, bool NOC_ = true, int TMAD_ = 0>
 struct Step3dCfg {
   static constexpr int WARPS = WARPS_, RY = RY_, MINB = MINB_, NT = 32 * WARPS_, TX = 64, TY = RY_ * WARPS_;
   static constexpr bool NOC = NOC_;
+  static constexpr int TMAD = TMAD_;
+  // arrays staged with their halo rows per mode: JACOBI r, dinv, p ; Z z, p ; PREC r, dinv ; HORNER w ; UPDPREC r, dinv, q ; INIT theta
+  __host__ __device__ static constexpr int narr(int mode) { return (mode == 0 || mode == 4) ? 3 : ((mode == 1 || mode == 2) ? 2 : 1); }
+  __host__ __device__ static constexpr size_t smem_bytes(int mode, size_t esz) {
+    return TMAD_ ? (size_t)WARPS_ * TMAD_ * (narr(mode) * (RY_ + 2) * 64 * esz + 8) : 0;
+  }
 };
 
 template <typename T, typename Cfg, int MODE>
@@ -116,6 +127,22 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
     }
   }
   bool stored_peer = false;
+  // ---- TMA staging (Cfg::TMAD >= 2): per-warp ring [stage][array][row][64] and one mbarrier per stage
+  constexpr int TMAD = Cfg::TMAD;
+  constexpr int NARR = Cfg::narr(MODE);
+  constexpr int CSLOT = NARR - 1;                       // slot of the third array (p_old / q) when there is one
+  MVTV_DYN_SMEM(smem_raw);
+  T *ring = reinterpret_cast<T *>(smem_raw) + (size_t)warp * (TMAD > 0 ? TMAD : 1) * NARR * NR * 64;
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(reinterpret_cast<T *>(smem_raw) + (size_t)Cfg::WARPS * TMAD * NARR * NR * 64) + warp * TMAD;
+  const int rowlen = min(64, m0 - xw);                  // vertices of the strip inside the mesh (even)
+  const int xl = xo - xw;                               // this lane's pair inside the staged row
+  if (TMAD > 0) {
+    if (lane == 0) {
+      for (int s_ = 0; s_ < TMAD; ++s_) mbar_init(&mbar[s_], 1);
+      mbar_init_fence();
+    }
+    __syncwarp();
+  }
   // NOC: boundary class bits of this lane's outputs within a plane (bit 0: axis 0, bit 1: axis 1)
   int cls[RY][2];
 #pragma unroll
@@ -140,9 +167,11 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
     const long long pb = (long long)(zs + 1) * dt.plane;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      ld2(rr + pb + rowoff[r], ra[r]);
-      if (STAGE_B) ld2(dinv + pb + rowoff[r], rb_[r]);
-      if (stage_c) ld2(p_in + pb + rowoff[r], rc[r]);
+      if (TMAD == 0) {
+        ld2(rr + pb + rowoff[r], ra[r]);
+        if (STAGE_B) ld2(dinv + pb + rowoff[r], rb_[r]);
+        if (stage_c) ld2(p_in + pb + rowoff[r], rc[r]);
+      }
       if (edge) {
         ha[r] = rr[pb + rowoff_h[r]];
         if (STAGE_B) hb[r] = dinv[pb + rowoff_h[r]];
@@ -162,6 +191,36 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
     }
   };
 
+  // TMA staging: plane zz goes into ring stage (zz - zfirst) % TMAD; every lane issues at most one row copy per pass of the loop
+  auto tma_issue = [&](int zz) {
+    if (TMAD == 0 || zz > zlast) return;
+    const int stg = (zz - zfirst) % (TMAD > 0 ? TMAD : 1);
+    const int zs = min(max(zz, zlo), zhi);
+    const long long pb = (long long)(zs + 1) * dt.plane + xw;
+    const int narr_now = (NARR == 3 || (MODE == STEP_Z)) ? (stage_c ? NARR : NARR - 1) : NARR;   // no p_old in the first iteration
+    if (lane == 0) mbar_expect_tx(&mbar[stg], (unsigned)(narr_now * NR * rowlen * sizeof(T)));
+    __syncwarp();
+    for (int c = lane; c < NARR * NR; c += 32) {
+      const int ai = c / NR, r = c - ai * NR;
+      if (ai >= narr_now) continue;
+      const int yy = min(max(y0 - 1 + r, 0), m1 - 1);
+      const T *src = (ai == 0) ? rr : ((ai == CSLOT && (NARR == 3 || MODE == STEP_Z)) ? p_in : dinv);
+      bulk_g2s(ring + ((size_t)(stg * NARR + ai) * NR + r) * 64, src + pb + (long long)yy * m0, (unsigned)(rowlen * sizeof(T)), &mbar[stg]);
+    }
+  };
+  auto tma_consume = [&](int zz) {
+    if (TMAD == 0) return;
+    const int k = zz - zfirst, stg = k % (TMAD > 0 ? TMAD : 1);
+    mbar_wait(&mbar[stg], (unsigned)((k / (TMAD > 0 ? TMAD : 1)) & 1));
+    const T *sp = ring + (size_t)stg * NARR * NR * 64 + xl;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      ld2(sp + (size_t)r * 64, ra[r]);
+      if (STAGE_B) ld2(sp + (size_t)(NR + r) * 64, rb_[r]);
+      if (stage_c && (NARR == 3 || MODE == STEP_Z)) ld2(sp + (size_t)(CSLOT * NR + r) * 64, rc[r]);
+    }
+  };
+
   T A0[RY][2], A1[RY][2], A2[RY][2], pcp[RY][2], cqp[RY][2], rcp[RY][2], dcp[RY][2];
 #pragma unroll
   for (int j = 0; j < RY; ++j)
@@ -169,8 +228,14 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
     for (int k = 0; k < 2; ++k) A0[j][k] = A1[j][k] = A2[j][k] = pcp[j][k] = cqp[j][k] = rcp[j][k] = dcp[j][k] = T(0);
   double red[3] = {0.0, 0.0, 0.0};   // [1]: r.r of STEP_UPDPREC / STEP_INIT, [2]: b.b of STEP_INIT
 
+  if (TMAD > 0) {
+#pragma unroll
+    for (int d_ = 0; d_ < (TMAD > 0 ? TMAD - 1 : 0); ++d_) tma_issue(zfirst + d_);
+  }
   load_plane(zfirst);
   for (int zz = zfirst; zz <= zlast; ++zz) {
+    tma_issue(zz + TMAD - 1);   // into the stage the previous plane has just left
+    tma_consume(zz);
     // ---- combine: p_new (z0, w) of plane zz on the RY+2 rows, at the pair and at the strip's halo element
     T v[NR][2], hv[NR], rown[RY][2], down[RY][2], cown[RY][2];
 #pragma unroll

@@ -509,6 +509,42 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif
 
+// ---- TMA bulk copies global -> shared, tracked by an mbarrier (cp.async.bulk: SASS UBLKCP; no tensor map is needed for
+// contiguous rows).  One thread arms the barrier with the byte count of a stage, any thread issues the copies, the consumers
+// wait for the stage's phase parity.  16-byte aligned addresses, sizes in multiples of 16 bytes.
+#ifdef MVTV_CUDA_EMU   // CPU emulator: the copy completes at once, the barrier is never waited for
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int) { *bar = 0; }
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *) { memcpy(smem_dst, gmem_src, bytes); }
+__device__ __forceinline__ void mbar_wait(unsigned long long *, unsigned) {}
+#else
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {   // make the initialised barriers visible to the async proxy
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+}
+#endif
+
 // MODE: what the staged arrays are and what leaves the kernel
 //   STEP_JACOBI  stage r, dinv, p_old : p = dinv.*r + beta*p_old ; writes p, q = M p ; reduces p.q
 //   STEP_Z       stage z, p_old       : p = z + beta*p_old       ; writes p, q = M p ; reduces p.q

@@ -166,7 +166,7 @@ struct mvtv_plan {
   int max_degree = 1;       // highest polynomial degree this plan's kernels implement
   int auto_degree = 1;      // what MVTV_PRECOND_AUTO picks once Jacobi needs more than 24 iterations (measured per family)
   bool fused_update = false;   // one GPU, strip kernels: k_cg_update fused with the first preconditioner pass (r out of place)
-  int tune_fuse3d = 0, tune_horner3d = 0, tune_init3d = 1;   // developer knob MVTV_TUNE: candidates still being measured
+  int tune_tma3d = 0, tune_init3d = 1;   // developer knob MVTV_TUNE: candidates still being measured
   void *r2 = nullptr;          // second residual buffer of the fused update (allocated on first use)
   void *ybuf = nullptr;        // third buffer of the Horner passes, degree >= 3 (allocated on first use; with world > 1 at plan creation)
   int zu_variant = -1;   // ZV_* when the compile-time block tables of k_zu_march match this plan, else -1 (gather kernel)
@@ -460,7 +460,7 @@ struct mvtv_plan {
     auto_degree = full ? 3 : 1;
     fused_update = full;
     // MVTV_TUNE="key=value,...": developer knob for A/B measurements of candidates that are still compiled in
-    // (fused=0|1, degree=1..4 for MVTV_PRECOND_AUTO, fuse3d / horner3d = tile candidate)
+    // (fused=0|1, degree=1..4 for MVTV_PRECOND_AUTO, tma3d=0|1: TMA staging of the 3-D strip kernels, init3d=0|1)
     if (const char *tune = getenv("MVTV_TUNE")) {
       std::string t(tune);
       size_t pos = 0;
@@ -474,8 +474,7 @@ struct mvtv_plan {
           const int v = atoi(kv.c_str() + eq + 1);
           if (k == "fused") fused_update = fused_update && v != 0;
           else if (k == "degree") auto_degree = std::max(1, std::min(v, max_degree));
-          else if (k == "fuse3d") tune_fuse3d = v;
-          else if (k == "horner3d") tune_horner3d = v;
+          else if (k == "tma3d") tune_tma3d = (v != 0 && (dt.m[0] * (long long)esz()) % 16 == 0) ? 1 : 0;   // 16-byte rows
           else if (k == "init3d") tune_init3d = v;
         }
         pos = end + 1;
@@ -872,15 +871,13 @@ using S2Step = Step2dCfg<4, 1, 4, 0>;
 using S2Prec = Step2dCfg<8, 1, 2, 4, true>;
 using S2Fuse = Fused2dCfg<8, 0>;
 constexpr int S2_HORNER_WARPS = 8, S2_HORNER_MINB = 3, S2_INIT_WARPS = 4;
-using S3Step = Step3dCfg<4, 4>;
-using S3Prec = Step3dCfg<4, 3>;
-// candidates of the two new modes (MVTV_TUNE=fuse3d=k / horner3d=k), to be fixed by the next measurement
-template <int K> struct S3FuseSel { using Cfg = Step3dCfg<4, 2>; };
-template <> struct S3FuseSel<1> { using Cfg = Step3dCfg<4, 3>; };
-template <> struct S3FuseSel<2> { using Cfg = Step3dCfg<8, 2>; };
-template <int K> struct S3HornerSel { using Cfg = Step3dCfg<4, 3>; };
-template <> struct S3HornerSel<1> { using Cfg = Step3dCfg<4, 4>; };
-template <> struct S3HornerSel<2> { using Cfg = Step3dCfg<4, 2>; };
+// tiles of the 3-D strip kernels; TMAD = 0: rows loaded into registers, 3: TMA bulk copies into a 3-stage per-warp ring
+template <int TMAD>
+struct S3Tiles {
+  using Step = Step3dCfg<4, 4, 0, true, TMAD>;
+  using Prec = Step3dCfg<4, 3, 0, true, TMAD>;     // also the Horner passes and the CG initialisation
+  using Fuse = Step3dCfg<4, 2, 0, true, TMAD>;     // 4 x 3 rows spills (255 registers), 8 x 2 measures the same
+};
 
 template <typename T, int P>
 int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int maxit, int deg, long long &inner, int &status) {
@@ -970,17 +967,14 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     nchunk = (dt.nz + zchunk_out - 1) / zchunk_out;
     return dim3(tiles, (unsigned)nchunk, 1);
   };
-  auto sel3 = [](int k, auto &&fn) {   // run fn with the candidate index as a compile-time constant
-    switch (k) {
-      case 1: fn(std::integral_constant<int, 1>{}); break;
-      case 2: fn(std::integral_constant<int, 2>{}); break;
-      default: fn(std::integral_constant<int, 0>{}); break;
-    }
+  auto with3 = [this](auto &&fn) {   // run fn with the 3-D tile set as a type
+    if (tune_tma3d) fn(S3Tiles<3>{});
+    else fn(S3Tiles<0>{});
   };
   // occupancy queries are per device and per kernel: cache them per (device, family, slot)
   struct Shapes { bool set = false; int occ[8] = {1, 1, 1, 1, 1, 1, 1, 1}; };
-  static Shapes shapes_dev[64][3][9];   // tile candidates have their own occupancies
-  Shapes &sh = shapes_dev[device & 63][fam][(tune_fuse3d % 3) * 3 + (tune_horner3d % 3)];
+  static Shapes shapes_dev[64][3][2];   // the TMA tile set has its own occupancies
+  Shapes &sh = shapes_dev[device & 63][fam][tune_tma3d & 1];
   enum { K_STEP_J = 0, K_STEP_Z = 1, K_PREC = 2, K_HORNER = 3, K_FUSED = 4, K_INIT = 5 };
   const size_t smem = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_JACOBI>();
   const size_t smem2 = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_Z>();
@@ -1009,14 +1003,22 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       }
     }
     if constexpr (HAS3D) {
-      if (fam == CGF_STRIP3D) {
-        sh.occ[K_STEP_J] = occ_of(k_cg_step3d<T, S3Step, STEP_JACOBI>, S3Step::NT, 0);
-        sh.occ[K_STEP_Z] = occ_of(k_cg_step3d<T, S3Step, STEP_Z>, S3Step::NT, 0);
-        sh.occ[K_PREC] = occ_of(k_cg_step3d<T, S3Prec, STEP_PREC>, S3Prec::NT, 0);
-        sh.occ[K_INIT] = occ_of(k_cg_step3d<T, S3Prec, STEP_INIT>, S3Prec::NT, 0);
-        sel3(tune_horner3d, [&](auto k) { using C3 = typename S3HornerSel<decltype(k)::value>::Cfg; sh.occ[K_HORNER] = occ_of(k_cg_step3d<T, C3, STEP_HORNER>, C3::NT, 0); });
-        sel3(tune_fuse3d, [&](auto k) { using C3 = typename S3FuseSel<decltype(k)::value>::Cfg; sh.occ[K_FUSED] = occ_of(k_cg_step3d<T, C3, STEP_UPDPREC>, C3::NT, 0); });
-      }
+      if (fam == CGF_STRIP3D)
+        with3([&](auto ts) {
+          using TS = decltype(ts);
+          auto occ3 = [&](auto kern, auto cfg, int mode) {
+            using C3 = decltype(cfg);
+            const size_t sm = C3::smem_bytes(mode, sizeof(T));
+            if (sm) MVTV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            return occ_of(kern, C3::NT, sm);
+          };
+          sh.occ[K_STEP_J] = occ3(k_cg_step3d<T, typename TS::Step, STEP_JACOBI>, typename TS::Step{}, STEP_JACOBI);
+          sh.occ[K_STEP_Z] = occ3(k_cg_step3d<T, typename TS::Step, STEP_Z>, typename TS::Step{}, STEP_Z);
+          sh.occ[K_PREC] = occ3(k_cg_step3d<T, typename TS::Prec, STEP_PREC>, typename TS::Prec{}, STEP_PREC);
+          sh.occ[K_INIT] = occ3(k_cg_step3d<T, typename TS::Prec, STEP_INIT>, typename TS::Prec{}, STEP_INIT);
+          sh.occ[K_HORNER] = occ3(k_cg_step3d<T, typename TS::Prec, STEP_HORNER>, typename TS::Prec{}, STEP_HORNER);
+          sh.occ[K_FUSED] = occ3(k_cg_step3d<T, typename TS::Fuse, STEP_UPDPREC>, typename TS::Fuse{}, STEP_UPDPREC);
+        });
     }
     sh.set = true;
   }
@@ -1027,10 +1029,10 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     tiles_horner = (unsigned)((m0 + 64 * S2_HORNER_WARPS - 1) / (64 * S2_HORNER_WARPS));
     tiles_fused = (unsigned)((m0 + S2Fuse::TX - 1) / S2Fuse::TX);
   } else if (fam == CGF_STRIP3D) {
-    tiles_step = (unsigned)(((m0 + S3Step::TX - 1) / S3Step::TX) * ((m1 + S3Step::TY - 1) / S3Step::TY));
-    tiles_prec = (unsigned)(((m0 + S3Prec::TX - 1) / S3Prec::TX) * ((m1 + S3Prec::TY - 1) / S3Prec::TY));
-    sel3(tune_horner3d, [&](auto k) { using C3 = typename S3HornerSel<decltype(k)::value>::Cfg; tiles_horner = (unsigned)(((m0 + C3::TX - 1) / C3::TX) * ((m1 + C3::TY - 1) / C3::TY)); });
-    sel3(tune_fuse3d, [&](auto k) { using C3 = typename S3FuseSel<decltype(k)::value>::Cfg; tiles_fused = (unsigned)(((m0 + C3::TX - 1) / C3::TX) * ((m1 + C3::TY - 1) / C3::TY)); });
+    using TS = S3Tiles<0>;   // the tile shapes do not depend on the staging
+    tiles_step = (unsigned)(((m0 + TS::Step::TX - 1) / TS::Step::TX) * ((m1 + TS::Step::TY - 1) / TS::Step::TY));
+    tiles_prec = tiles_horner = (unsigned)(((m0 + TS::Prec::TX - 1) / TS::Prec::TX) * ((m1 + TS::Prec::TY - 1) / TS::Prec::TY));
+    tiles_fused = (unsigned)(((m0 + TS::Fuse::TX - 1) / TS::Fuse::TX) * ((m1 + TS::Fuse::TY - 1) / TS::Fuse::TY));
   } else {
     tiles_step = tiles_prec = (unsigned)(((m0 + Cfg::TX - 1) / Cfg::TX) * ((m1 + Cfg::TY - 1) / Cfg::TY) * ((m2 + Cfg::TW - 1) / Cfg::TW));
   }
@@ -1062,7 +1064,10 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     if (fam == CGF_STRIP3D && tune_init3d) {   // marching / shuffle form (STEP_INIT of cg_step3d.cuh)
       int zc_init = 1;
       const dim3 gi = chunking(tiles_prec, sh.occ[K_INIT], zc_init);
-      k_cg_step3d<T, S3Prec, STEP_INIT><<<gi, S3Prec::NT, 0, stream>>>(dt, st, a, RedBuf{partials, counters + 1}, zc_init);
+      with3([&](auto ts) {
+        using C3 = typename decltype(ts)::Prec;
+        k_cg_step3d<T, C3, STEP_INIT><<<gi, C3::NT, C3::smem_bytes(STEP_INIT, sizeof(T)), stream>>>(dt, st, a, RedBuf{partials, counters + 1}, zc_init);
+      });
       init_done = true;
     }
   }
@@ -1100,7 +1105,10 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     }
     if constexpr (HAS3D) {
       if (fam == CGF_STRIP3D) {
-        k_cg_step3d<T, S3Prec, STEP_PREC><<<gs_prec, S3Prec::NT, 0, stream>>>(dt, st, a, rbp, zc_prec);
+        with3([&](auto ts) {
+          using C3 = typename decltype(ts)::Prec;
+          k_cg_step3d<T, C3, STEP_PREC><<<gs_prec, C3::NT, C3::smem_bytes(STEP_PREC, sizeof(T)), stream>>>(dt, st, a, rbp, zc_prec);
+        });
         done = true;
       }
     }
@@ -1125,9 +1133,9 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       }
       if constexpr (HAS3D) {
         if (fam == CGF_STRIP3D)
-          sel3(tune_horner3d, [&](auto k) {
-            using C3 = typename S3HornerSel<decltype(k)::value>::Cfg;
-            k_cg_step3d<T, C3, STEP_HORNER><<<gs_horner, C3::NT, 0, stream>>>(dt, st, a, rbp, zc_horner);
+          with3([&](auto ts) {
+            using C3 = typename decltype(ts)::Prec;
+            k_cg_step3d<T, C3, STEP_HORNER><<<gs_horner, C3::NT, C3::smem_bytes(STEP_HORNER, sizeof(T)), stream>>>(dt, st, a, rbp, zc_horner);
           });
       }
       launches += 1;
@@ -1159,8 +1167,11 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     }
     if constexpr (HAS3D) {
       if (fam == CGF_STRIP3D) {
-        if (deg) k_cg_step3d<T, S3Step, STEP_Z><<<gs, S3Step::NT, 0, stream>>>(dt, st, a, rbs, zc_step);
-        else k_cg_step3d<T, S3Step, STEP_JACOBI><<<gs, S3Step::NT, 0, stream>>>(dt, st, a, rbs, zc_step);
+        with3([&](auto ts) {
+          using C3 = typename decltype(ts)::Step;
+          if (deg) k_cg_step3d<T, C3, STEP_Z><<<gs, C3::NT, C3::smem_bytes(STEP_Z, sizeof(T)), stream>>>(dt, st, a, rbs, zc_step);
+          else k_cg_step3d<T, C3, STEP_JACOBI><<<gs, C3::NT, C3::smem_bytes(STEP_JACOBI, sizeof(T)), stream>>>(dt, st, a, rbs, zc_step);
+        });
         done = true;
       }
     }
@@ -1194,9 +1205,9 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       }
       if constexpr (HAS3D) {
         if (fam == CGF_STRIP3D)
-          sel3(tune_fuse3d, [&](auto k) {
-            using C3 = typename S3FuseSel<decltype(k)::value>::Cfg;
-            k_cg_step3d<T, C3, STEP_UPDPREC><<<gs_fused, C3::NT, 0, stream>>>(dt, st, a, rbu, zc_fused);
+          with3([&](auto ts) {
+            using C3 = typename decltype(ts)::Fuse;
+            k_cg_step3d<T, C3, STEP_UPDPREC><<<gs_fused, C3::NT, C3::smem_bytes(STEP_UPDPREC, sizeof(T)), stream>>>(dt, st, a, rbu, zc_fused);
           });
       }
       launches += 1;
