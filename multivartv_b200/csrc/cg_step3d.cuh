@@ -412,11 +412,17 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   }
   if (MODE == STEP_UPDPREC) {   // {r.z, r.r} of the next parity, the iteration count advances (several GPUs: folded commits only)
     double r2[2] = {red[0], red[1]};
-    grid_reduce<2, 2>(r2, rb, [S, peer, sr, fin, signal_z](const double (&res)[2]) {
+    const int defer = a.defer_rr;
+    grid_reduce<2, 2>(r2, rb, [S, peer, sr, fin, defer, signal_z](const double (&res)[2]) {
       double v[2] = {res[0], res[1]};
       if (peer) {
         signal_z();
         peer_post(*peer, sr, res, 2);
+        if (!fin && defer) {   // r.r is collected by the last Horner pass; until then the slot must not read as converged
+          v[1] = 1.0e300;
+          cg_commit_update_prec(S, v + 1);
+          return;
+        }
         peer_wait_sum(*peer, sr, v, 2);
       }
       if (fin) cg_commit_update(S, v);
@@ -427,7 +433,8 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   double r1[1] = {red[0]};
   if (MODE == STEP_HORNER || MODE == STEP_PREC) {
     if (!fin && !peer) return;   // one GPU, not the last pass: nothing to reduce, nobody to signal
-    grid_reduce<1, 1>(r1, rb, [S, raw, peer, sr, fold, fin, signal_z](const double (&res)[1]) {
+    const unsigned long long srr = a.seq_rr_pending;
+    grid_reduce<1, 1>(r1, rb, [S, raw, peer, sr, srr, fold, fin, signal_z](const double (&res)[1]) {
       if (peer) {
         signal_z();
         if (!fin) return;
@@ -436,6 +443,11 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
           double v[1];
           peer_wait_sum(*peer, sr, v, 1);
           cg_commit_rz(S, v);
+          if (srr) {  // the fused update's r.r of this iteration (posted, not yet summed)
+            double w[2];
+            peer_wait_sum(*peer, srr, w, 2);
+            S[2 * (((int)S[CS_ITERS]) & 1) + 1] = w[1];
+          }
         }
       } else if (raw) raw[0] = res[0];
       else cg_commit_rz(S, res);

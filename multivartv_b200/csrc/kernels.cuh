@@ -319,6 +319,11 @@ struct CgArgs {
   int final_pass = 1;        // the pass that produces z also reduces r.z
   T *y = nullptr;
   unsigned long long seq_zin = 0, seq_zout = 0;   // k_cg_step3d: z-flag event this launch needs / posts (see PeerTab)
+  // several GPUs, degree >= 2: the fused update only POSTS its partial r.r (event seq_red) and advances the iteration count;
+  // the last Horner pass of the iteration collects it together with its own r.z (seq_rr_pending = that event, 0 = none),
+  // so an iteration has two world-wide rendezvous (p.q ; r.z + r.r) whatever the degree
+  unsigned long long seq_rr_pending = 0;
+  int defer_rr = 0;
   // fused update + first preconditioner pass (k_cg_updprec*): r is updated OUT OF PLACE, the buffer holding the
   // current residual is selected by the parity of the iterations performed (r2 == nullptr: r is updated in place)
   T *r2 = nullptr;

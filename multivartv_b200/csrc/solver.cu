@@ -166,7 +166,7 @@ struct mvtv_plan {
   int max_degree = 1;       // highest polynomial degree this plan's kernels implement
   int auto_degree = 1;      // what MVTV_PRECOND_AUTO picks once Jacobi needs more than 24 iterations (measured per family)
   bool fused_update = false;   // one GPU, strip kernels: k_cg_update fused with the first preconditioner pass (r out of place)
-  int tune_tma3d = 0, tune_init3d = 1;   // developer knob MVTV_TUNE: candidates still being measured
+  int tune_init3d = 1, tune_defer_rr = 1;   // developer knob MVTV_TUNE: candidates still being measured
   void *r2 = nullptr;          // second residual buffer of the fused update (allocated on first use)
   void *ybuf = nullptr;        // third buffer of the Horner passes, degree >= 3 (allocated on first use; with world > 1 at plan creation)
   int zu_variant = -1;   // ZV_* when the compile-time block tables of k_zu_march match this plan, else -1 (gather kernel)
@@ -460,7 +460,7 @@ struct mvtv_plan {
     auto_degree = full ? 3 : 1;
     fused_update = full;
     // MVTV_TUNE="key=value,...": developer knob for A/B measurements of candidates that are still compiled in
-    // (fused=0|1, degree=1..4 for MVTV_PRECOND_AUTO, tma3d=0|1: TMA staging of the 3-D strip kernels, init3d=0|1)
+    // (fused=0|1, degree=1..4 for MVTV_PRECOND_AUTO, init3d=0|1: gather / marching CG initialisation, defer_rr=0|1)
     if (const char *tune = getenv("MVTV_TUNE")) {
       std::string t(tune);
       size_t pos = 0;
@@ -474,8 +474,8 @@ struct mvtv_plan {
           const int v = atoi(kv.c_str() + eq + 1);
           if (k == "fused") fused_update = fused_update && v != 0;
           else if (k == "degree") auto_degree = std::max(1, std::min(v, max_degree));
-          else if (k == "tma3d") tune_tma3d = (v != 0 && (dt.m[0] * (long long)esz()) % 16 == 0) ? 1 : 0;   // 16-byte rows
           else if (k == "init3d") tune_init3d = v;
+          else if (k == "defer_rr") tune_defer_rr = v;
         }
         pos = end + 1;
       }
@@ -871,12 +871,16 @@ using S2Step = Step2dCfg<4, 1, 4, 0>;
 using S2Prec = Step2dCfg<8, 1, 2, 4, true>;
 using S2Fuse = Fused2dCfg<8, 0>;
 constexpr int S2_HORNER_WARPS = 8, S2_HORNER_MINB = 3, S2_INIT_WARPS = 4;
-// tiles of the 3-D strip kernels; TMAD = 0: rows loaded into registers, 3: TMA bulk copies into a 3-stage per-warp ring
-template <int TMAD>
+// tiles of the 3-D strip kernels.  TMA staging (Step3dCfg::TMAD = 3: cp.async.bulk row copies into a per-warp ring) was measured
+// on every mode (profiles/r2d_probe3_tma.log, 512^3): it loses 5 / 13 / 25 % on the direction, fused-update and Horner kernels --
+// their rows are consumed once, the extra shared-memory hop and the 512-byte copy granularity cost more than the deeper prefetch
+// gains -- and wins on the CG initialisation (2.0 against 3.0 ms), whose five own-row side streams compete with the staged rows
+// for registers; so only that mode uses it.
 struct S3Tiles {
-  using Step = Step3dCfg<4, 4, 0, true, TMAD>;
-  using Prec = Step3dCfg<4, 3, 0, true, TMAD>;     // also the Horner passes and the CG initialisation
-  using Fuse = Step3dCfg<4, 2, 0, true, TMAD>;     // 4 x 3 rows spills (255 registers), 8 x 2 measures the same
+  using Step = Step3dCfg<4, 4>;
+  using Prec = Step3dCfg<4, 3>;                    // also the Horner passes
+  using Fuse = Step3dCfg<4, 2>;                    // 4 x 3 rows spills (255 registers), 8 x 2 measures the same
+  using Init = Step3dCfg<4, 3, 0, true, 3>;        // TMA staging of theta's rows
 };
 
 template <typename T, int P>
@@ -933,6 +937,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     return rot[deg][j - 1];
   };
   unsigned long long z_event = 0;   // z-flag event of the latest exported planes (several GPUs)
+  unsigned long long rr_pending = 0;   // reduction event of a fused update whose r.r the last Horner pass still has to collect
   // coefficients c_0 .. c_d of the degree-d polynomial P in D^-1 M whose residual 1 - t P(t) is the Chebyshev polynomial
   // T_{d+1} on [bmax/kappa, bmax]; Horner form: w_1 = c_d A z0 + c_{d-1} z0, w_k = A w_{k-1} + c_{d-k} z0, z = w_d
   double hc[8] = {0};
@@ -967,14 +972,13 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     nchunk = (dt.nz + zchunk_out - 1) / zchunk_out;
     return dim3(tiles, (unsigned)nchunk, 1);
   };
-  auto with3 = [this](auto &&fn) {   // run fn with the 3-D tile set as a type
-    if (tune_tma3d) fn(S3Tiles<3>{});
-    else fn(S3Tiles<0>{});
-  };
+  auto with3 = [](auto &&fn) { fn(S3Tiles{}); };   // run fn with the 3-D tile set as a type
+  // the marching CG initialisation stages rows with 16-byte bulk copies: fp32 meshes need m0 % 4 == 0
+  const bool init3d = (fam == CGF_STRIP3D) && tune_init3d && ((dt.m[0] * (long long)esz()) % 16 == 0);
   // occupancy queries are per device and per kernel: cache them per (device, family, slot)
   struct Shapes { bool set = false; int occ[8] = {1, 1, 1, 1, 1, 1, 1, 1}; };
-  static Shapes shapes_dev[64][3][2];   // the TMA tile set has its own occupancies
-  Shapes &sh = shapes_dev[device & 63][fam][tune_tma3d & 1];
+  static Shapes shapes_dev[64][3];
+  Shapes &sh = shapes_dev[device & 63][fam];
   enum { K_STEP_J = 0, K_STEP_Z = 1, K_PREC = 2, K_HORNER = 3, K_FUSED = 4, K_INIT = 5 };
   const size_t smem = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_JACOBI>();
   const size_t smem2 = sizeof(T) * (size_t)Cfg::template smem_elems<STEP_Z>();
@@ -1015,7 +1019,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
           sh.occ[K_STEP_J] = occ3(k_cg_step3d<T, typename TS::Step, STEP_JACOBI>, typename TS::Step{}, STEP_JACOBI);
           sh.occ[K_STEP_Z] = occ3(k_cg_step3d<T, typename TS::Step, STEP_Z>, typename TS::Step{}, STEP_Z);
           sh.occ[K_PREC] = occ3(k_cg_step3d<T, typename TS::Prec, STEP_PREC>, typename TS::Prec{}, STEP_PREC);
-          sh.occ[K_INIT] = occ3(k_cg_step3d<T, typename TS::Prec, STEP_INIT>, typename TS::Prec{}, STEP_INIT);
+          sh.occ[K_INIT] = occ3(k_cg_step3d<T, typename TS::Init, STEP_INIT>, typename TS::Init{}, STEP_INIT);
           sh.occ[K_HORNER] = occ3(k_cg_step3d<T, typename TS::Prec, STEP_HORNER>, typename TS::Prec{}, STEP_HORNER);
           sh.occ[K_FUSED] = occ3(k_cg_step3d<T, typename TS::Fuse, STEP_UPDPREC>, typename TS::Fuse{}, STEP_UPDPREC);
         });
@@ -1029,7 +1033,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     tiles_horner = (unsigned)((m0 + 64 * S2_HORNER_WARPS - 1) / (64 * S2_HORNER_WARPS));
     tiles_fused = (unsigned)((m0 + S2Fuse::TX - 1) / S2Fuse::TX);
   } else if (fam == CGF_STRIP3D) {
-    using TS = S3Tiles<0>;   // the tile shapes do not depend on the staging
+    using TS = S3Tiles;
     tiles_step = (unsigned)(((m0 + TS::Step::TX - 1) / TS::Step::TX) * ((m1 + TS::Step::TY - 1) / TS::Step::TY));
     tiles_prec = tiles_horner = (unsigned)(((m0 + TS::Prec::TX - 1) / TS::Prec::TX) * ((m1 + TS::Prec::TY - 1) / TS::Prec::TY));
     tiles_fused = (unsigned)(((m0 + TS::Fuse::TX - 1) / TS::Fuse::TX) * ((m1 + TS::Fuse::TY - 1) / TS::Fuse::TY));
@@ -1061,11 +1065,11 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
     }
   }
   if constexpr (HAS3D) {
-    if (fam == CGF_STRIP3D && tune_init3d) {   // marching / shuffle form (STEP_INIT of cg_step3d.cuh)
+    if (init3d) {   // marching / shuffle form with TMA-staged rows (STEP_INIT of cg_step3d.cuh): 2.0 against 3.6 ms on 512^3
       int zc_init = 1;
       const dim3 gi = chunking(tiles_prec, sh.occ[K_INIT], zc_init);
       with3([&](auto ts) {
-        using C3 = typename decltype(ts)::Prec;
+        using C3 = typename decltype(ts)::Init;
         k_cg_step3d<T, C3, STEP_INIT><<<gi, C3::NT, C3::smem_bytes(STEP_INIT, sizeof(T)), stream>>>(dt, st, a, RedBuf{partials, counters + 1}, zc_init);
       });
       init_done = true;
@@ -1122,7 +1126,11 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       a.w_in_scr = wsel(j - 1);
       a.seq_zin = z_event;
       a.seq_zout = z_event = ++zhalo_seq;
-      if (j == deg) a.seq_red = ++red_seq;
+      if (j == deg) {
+        a.seq_red = ++red_seq;
+        a.seq_rr_pending = rr_pending;
+        rr_pending = 0;
+      }
       a.final_pass = (j == deg) ? 1 : 0;
       a.pc0 = hc[deg - j];
       a.pc1 = 0.0;
@@ -1197,6 +1205,8 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       a.w_in_scr = 0;
       a.seq_zin = z_event;                        // ghost planes of q
       a.seq_zout = z_event = ++zhalo_seq;
+      a.defer_rr = (d_peer && deg >= 2 && tune_defer_rr) ? 1 : 0;
+      rr_pending = a.defer_rr ? a.seq_red : 0;
       a.final_pass = (deg == 1) ? 1 : 0;
       a.pc0 = hc[deg - 1];
       a.pc1 = hc[deg];

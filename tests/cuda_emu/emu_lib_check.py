@@ -168,8 +168,8 @@ def main():
         sweep([130, 33], 3000, 7, 2, [cases2[1], cases2[3], cases2[6]])
     cases3 = [({}, "jacobi", s3, 0), ({}, "cheb1", s3, 1), ({}, "cheb2", s3, 2), ({}, "cheb3", s3, 3), ({}, "cheb4", s3, 4),
               (R, "jacobi", ring, 0), (R, "cheb1", ring, 1), ({"EMU_NSM": "16"}, "cheb3", s3, 3), ({"EMU_NSM": "2", "EMU_OCC": "1"}, "cheb2", s3, 2),
-              ({"MVTV_TUNE": "tma3d=1"}, "jacobi", s3, 0), ({"MVTV_TUNE": "tma3d=1"}, "cheb1", s3, 1), ({"MVTV_TUNE": "tma3d=1"}, "cheb3", s3, 3),
-              ({"MVTV_TUNE": "tma3d=1,fused=0"}, "cheb2", s3, 2), ({"MVTV_TUNE": "tma3d=1,init3d=0", "EMU_NSM": "3"}, "cheb4", s3, 4)]
+              ({"MVTV_TUNE": "init3d=0"}, "jacobi", s3, 0), ({"MVTV_TUNE": "fused=0"}, "cheb1", s3, 1), ({"MVTV_TUNE": "init3d=0"}, "cheb3", s3, 3),
+              ({"MVTV_TUNE": "fused=0"}, "cheb2", s3, 2), ({"MVTV_TUNE": "init3d=0,fused=0", "EMU_NSM": "3"}, "cheb4", s3, 4)]
     sweep([16, 6, 34], 3000, 2, 2, (cases3[:5] + cases3[9:12]) if quick else cases3, variant=1)   # non-cubic: the intended operator variant
     if not quick:
         sweep([12, 12, 12], 1500, 3, 2, [cases3[1], cases3[3], cases3[6], cases3[7]])
