@@ -582,6 +582,11 @@ def run_ours(args):
             if args.precond != "jacobi":
                 line["classical_cg"] = small_block(run_workload(mv, args, args.workload, None, 0, 1, local_rank, mv.PRECOND_JACOBI,
                                                                 "jacobi", half, args.warmup, with_e2e=False))
+                # SURVEY 8(d)'s byte formula describes classical (Jacobi) CG: its fraction for that configuration sits beside the
+                # default's, whose polynomial preconditioner lowers J -- and with it both the time per pass and the formula's bytes
+                if line.get("roofline") and line["classical_cg"].get("pass"):
+                    line["roofline"]["pass_classical_cg"] = dict(line["classical_cg"]["pass"], ms_per_step=line["classical_cg"]["ms_per_step"],
+                                                                 inner_cg_iters_per_pass=line["classical_cg"]["inner_cg_iters_per_pass"])
             for other in ("cfg2", "cfg4"):
                 if other != args.workload and args.workload == "cfg3":
                     line[other] = small_block(run_workload(mv, args, other, None, 0, 1, local_rank, precond, args.precond,

@@ -460,7 +460,7 @@ struct mvtv_plan {
     auto_degree = full ? 3 : 1;
     fused_update = full;
     // MVTV_TUNE="key=value,...": developer knob for A/B measurements of candidates that are still compiled in
-    // (fused=0|1, degree=1..4 for MVTV_PRECOND_AUTO, init3d=0|1: gather / marching CG initialisation, defer_rr=0|1)
+    // (fused=0|1, degree=1..4 for MVTV_PRECOND_AUTO, init3d=0|1: gather / marching CG initialisation, defer_rr=0|1, kappa=<interval ratio of the polynomial>)
     if (const char *tune = getenv("MVTV_TUNE")) {
       std::string t(tune);
       size_t pos = 0;
@@ -476,6 +476,7 @@ struct mvtv_plan {
           else if (k == "degree") auto_degree = std::max(1, std::min(v, max_degree));
           else if (k == "init3d") tune_init3d = v;
           else if (k == "defer_rr") tune_defer_rr = v;
+          else if (k == "kappa") cheb_kappa = std::max(2, v);
         }
         pos = end + 1;
       }
