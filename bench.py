@@ -430,7 +430,15 @@ def run_workload(mv, args, name, dist, rank, world, local_rank, precond, tag, st
     roof = None
     if dom:
         tot_ms = sum(s["total_ms"] for s in stages.values())
-        roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+        fam = kernels["cg_step"]
+        strip = fam != "k_cg_step"
+        fusedk = bool(kernels.get("fused_update")) and deg >= 1
+        kname = {"zu": kernels["zu"], "cg_init": (fam + "<STEP_INIT>") if fam == "k_cg_step3d" else ("k_cg_init2d" if strip else "k_cg_init"),
+                 "cg_step": fam + ("<STEP_Z>" if deg else "<STEP_JACOBI>"),
+                 "cg_update": ((fam + "<STEP_UPDPREC>") if fam == "k_cg_step3d" else "k_cg_updprec2d") if fusedk else "k_cg_update",
+                 "cg_prec": (((fam + "<STEP_HORNER>") if fam == "k_cg_step3d" else "k_cg_horner2d") + " x %d per CG iteration" % (deg - 1)) if (fusedk and deg >= 2)
+                            else fam + "<STEP_PREC>"}[dom]
+        roof = {"bound": "hbm", "kernel": kname, "kernel_class": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": stages[dom]["frac"], "traffic": ncu_traffic(name, dom, kernels, world, dtype),
                 "alg_bytes_per_launch": stages[dom]["alg_bytes_per_launch_group"], "avg_launch_ms": stages[dom]["avg_ms"],
                 "peak_source": peak_src, "share_of_step": stages[dom]["total_ms"] / max(tot_ms, 1e-9),
