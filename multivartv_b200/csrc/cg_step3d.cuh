@@ -389,16 +389,16 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   auto signal_z = [peer, szo, post_z]() {
     if (!post_z) return;
     __threadfence_system();
-    if (peer->has_lo) st_release_sys(peer->zflag_at_prev, szo);
-    if (peer->has_hi) st_release_sys(peer->zflag_at_next, szo);
+    if (peer->has_lo) st_flag_sys(peer->zflag_at_prev, szo);
+    if (peer->has_hi) st_flag_sys(peer->zflag_at_next, szo);
   };
   if (MODE == STEP_INIT) {      // {r.z, r.r, b.b}; r's ghost planes are posted on the halo flags
     const unsigned long long sh = a.seq_halo;
     grid_reduce<3, 3>(red, rb, [S, raw, peer, sr, sh, fold](const double (&res)[3]) {
       if (peer) {
         __threadfence_system();
-        if (peer->has_lo) st_release_sys(peer->hflag_at_prev, sh);
-        if (peer->has_hi) st_release_sys(peer->hflag_at_next, sh);
+        if (peer->has_lo) st_flag_sys(peer->hflag_at_prev, sh);
+        if (peer->has_hi) st_flag_sys(peer->hflag_at_next, sh);
         peer_post(*peer, sr, res, 3);
         if (fold) {   // what k_cg_peer_commit_init does
           double v[3];

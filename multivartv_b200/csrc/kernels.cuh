@@ -235,6 +235,7 @@ enum { PW_Z = 0, PW_P0 = 1, PW_P1 = 2, PW_Y = 3 };
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void st_relaxed_sys(double *p, double v) { __atomic_store(p, &v, __ATOMIC_RELAXED); }
+__device__ __forceinline__ void st_flag_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 __device__ __forceinline__ double ld_relaxed_sys(const double *p) { double v; __atomic_load(p, &v, __ATOMIC_RELAXED); return v; }
 #else
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -247,6 +248,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 __device__ __forceinline__ void st_relaxed_sys(double *p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// flag store of a release PATTERN: the caller has executed __threadfence_system() after the data stores; several flags (one
+// per peer) then cost one system-scope fence instead of one per st.release
+__device__ __forceinline__ void st_flag_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ double ld_relaxed_sys(const double *p) {
   double v;
@@ -271,7 +277,7 @@ __device__ __forceinline__ void peer_post(const PeerTab &pt, unsigned long long 
   for (int j = 0; j < pt.world; ++j)
     for (int k = 0; k < n; ++k) st_relaxed_sys(pt.slots[j] + (slot * MVTV_PEER_MAXW + pt.rank) * MVTV_PEER_NVAL + k, v[k]);
   __threadfence_system();
-  for (int j = 0; j < pt.world; ++j) st_release_sys(pt.flags[j] + slot * MVTV_PEER_MAXW + pt.rank, seq);
+  for (int j = 0; j < pt.world; ++j) st_flag_sys(pt.flags[j] + slot * MVTV_PEER_MAXW + pt.rank, seq);
 }
 // single thread: wait for every rank's partials of event `seq`, add them in rank order
 __device__ __forceinline__ void peer_wait_sum(const PeerTab &pt, unsigned long long seq, double *out, int n) {

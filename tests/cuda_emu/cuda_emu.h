@@ -215,7 +215,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, std::function<void(
 inline void __syncthreads() { ::cuda_emu::sync_block(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { ::cuda_emu::sync_warp(); }
 inline void __threadfence() {}
-inline void __threadfence_system() {}
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }   // ranks are host threads: a real fence
 inline long long clock64() {   // ~2 ticks per nanosecond, so that peer_spin's time-out (kernels.cuh) also ends a stuck emulated wait
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);

@@ -605,16 +605,17 @@ def test_config2_full_size_parity(mv):
 
 def test_config3_config4_bounded_parity(mv):
     """BASELINE configs[2] (3-D, half a point per vertex, reference operator) on a 128^3 mesh and configs[3] (4-D, n = N) on a
-    32^4 mesh, 3 passes against the live oracle: same checks.  The full 512^3 / 96^4 meshes are test_fullsize_digests."""
+    32^4 mesh, 3 passes against the live oracle: same checks.  Larger meshes of the same families: test_large_mesh_digests."""
     _fullsize_case(mv, [128, 128, 128], 1 << 20, 3, (mv.PRECOND_CHEB1, mv.PRECOND_AUTO))
     _fullsize_case(mv, [32, 32, 32, 32], 32 ** 4, 3, (mv.PRECOND_CHEB1, mv.PRECOND_AUTO))
 
 
-@pytest.mark.parametrize("name", ["cfg3", "cfg4"])
-def test_fullsize_digests(mv, name):
-    """BASELINE configs[2] / configs[3] at their stated sizes (512^3 with n = 2^26, 96^4 with n = N; bench.py's inputs), 3 RCPP
-    passes of the CUDA path against the digest of the CPU oracle's run of the same problem (tests/golden/make_fullsize_digest.py:
-    every 509th vertex of theta, every 3571st row of u, Counter, rho): identical Counter, theta <= 1e-9, u <= 1e-8, rho equal."""
+@pytest.mark.parametrize("name", ["cfg3_256", "cfg4_64", "cfg3", "cfg4"])
+def test_large_mesh_digests(mv, name):
+    """BASELINE configs[2] / configs[3] (bench.py's inputs) on 256^3 with n = 2^23 and on 64^4 with n = N -- and on the full 512^3 /
+    96^4 meshes where their digests have been generated (the oracle needs ~60 GB for those) -- 3 RCPP passes of the CUDA path
+    against the digest of the CPU oracle's run of the same problem (tests/golden/make_fullsize_digest.py: every 509th vertex of
+    theta, every 3571st row of u, Counter, rho, sum(theta)): identical Counter, theta <= 1e-9, u <= 1e-8, rho equal."""
     import os
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_%s_digest.npz" % name)
     if not os.path.exists(path):
@@ -632,3 +633,33 @@ def test_fullsize_digests(mv, name):
     eu = float(np.abs(out["u"][::int(g["stride_u"])] - g["u"]).max())
     assert et <= FP64_TOL and eu <= 1e-8, (name, et, eu)
     assert abs(float(out["theta"].sum()) - float(g["theta_sum"])) <= 1e-9 * out["theta"].size
+
+
+def test_full_size_cross_checks(mv, monkeypatch):
+    """BASELINE configs[2] and configs[3] at their STATED sizes (512^3 with n = 2^26; 96^4 with n = N), where the CPU oracle does not
+    fit a test (~60 GB, hours): independent implementations inside the library must agree on 3 RCPP passes -- 512^3: the strip
+    kernels (fused update, Horner degree 3, TMA-staged initialisation) against the shared-memory ring kernels with the separate
+    update and degree 1 (MVTV_STEP=ring); 96^4: the marching z/u kernel against the gather-form one (MVTV_ZU_KERNEL=gather).  Same
+    Counter and rho, theta within 1e-10, u within 1e-9.  (MVTV_TEST_TINY=1 shrinks the meshes: dry runs on the CPU emulator.)"""
+    import os
+    tiny = os.environ.get("MVTV_TEST_TINY") == "1"
+    for dims, n, env in (([512, 512, 512] if not tiny else [16, 16, 12], 1 << 26 if not tiny else 2000, ("MVTV_STEP", "ring")),
+                         ([96, 96, 96, 96] if not tiny else [6, 6, 6, 6], 96 ** 4 if not tiny else 1500, ("MVTV_ZU_KERNEL", "gather"))):
+        x, y = _bench_points(n, len(dims))
+        axes = [np.linspace(0.0, 1.0, d) for d in dims]
+        res = []
+        for alt in (False, True):
+            if alt:
+                monkeypatch.setenv(*env)
+            with mv.Plan(dims) as pl:
+                pl.set_points(x, y, axes)
+                res.append(pl.solve(1.0, mode="rcpp", max_passes=3, want_u=True, want_fitted=False, raise_on_nonconvergence=False))
+                res[-1]["kernels"] = pl.describe()
+            monkeypatch.delenv(env[0], raising=False)
+        a, b = res
+        assert a["kernels"] != b["kernels"] or env[0] == "MVTV_ZU_KERNEL"
+        assert a["counter"] == b["counter"] and a["rho"] == b["rho"]
+        assert np.abs(a["theta"] - b["theta"]).max() <= 1e-10, (dims, np.abs(a["theta"] - b["theta"]).max())
+        assert np.abs(a["u"] - b["u"]).max() <= 1e-9, (dims, np.abs(a["u"] - b["u"]).max())
+        assert np.isfinite(a["theta"]).all() and abs(a["theta"].mean() - y.mean()) < 0.05
+        del x, y, res, a, b
