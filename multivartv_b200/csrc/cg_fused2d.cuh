@@ -1,5 +1,6 @@
 // k_cg_updprec2d: CG vector update fused with the polynomial preconditioner, 2-D meshes, single GPU
-// (EXPERIMENTAL: opt-in with MVTV_FUSE_UPDPREC=1; logic-checked on the CPU SIMT emulator, not yet run on a GPU).
+// (the default on 2-D meshes with an even m0 on one GPU; 4096^2: 193 us against 137 + 87 us for the separate kernels,
+// profiles/r2b_probe2.log).
 //
 // One CG iteration with MVTV_PRECOND_CHEB1 is   p = z + beta p, q = M p, p.q      (k_cg_step2d<STEP_Z>,   5 N words)
 //                                               theta += a p, r -= a q, r.r       (k_cg_update,           6 N words)
@@ -7,11 +8,12 @@
 // The last two share r: fused, r_new is formed in registers (also on the strip's halo element and on the chunk's two halo
 // rows, which needs q there -- available on one GPU, where q is a full vector), fed straight into the preconditioner's
 // stencil, and written once.  Reads theta, p, r, q, dinv; writes theta, r, z: 8 N words instead of 9 N, one launch and one
-// grid reduction less per iteration.  r is updated OUT OF PLACE (r_in = rbuf[iters & 1], r_out the other buffer): a CTA reads
+// grid reduction less per iteration.  r is updated OUT OF PLACE (CgArgs::r / r2 selected by the parity of the iterations): a CTA reads
 // the rows next to its chunk as halo while their owner rewrites them.  theta is updated in place (no halo reads).
 // Structure as k_cg_step2d: a warp owns a strip of 64 vertices (two per lane), x-neighbours by shuffle, march along the last
 // axis with three accumulator sets in registers.  Scalars: alpha = r.z / p.q of the current parity; the epilogue commits
-// {r.z, r.r} of the next parity and advances the iteration count (cg_commit_update).
+// {r.z, r.r} of the next parity and advances the iteration count (cg_commit_update); with a polynomial of degree >= 2 this is
+// the first Horner pass (output buffer CgArgs::w_out_scr) and r.z comes from the last one.
 #pragma once
 #include "cg_step2d.cuh"
 

@@ -1,15 +1,13 @@
-// k_cg_horner2d: polynomial preconditioner of degree >= 2 for the x-update CG on 2-D meshes, one GPU
-// (EXPERIMENTAL: opt-in with MVTV_CHEB_DEGREE=2..4; logic-checked on the CPU SIMT emulator -- tests/cuda_emu/emu_solve.cpp: degree 1 equals k_cg_step2d<STEP_PREC>,
-// degrees 2..4 give the same theta / u in fewer CG iterations -- but not yet run on a GPU).
+// k_cg_horner2d: the Horner passes of the polynomial preconditioner of degree >= 2 on 2-D meshes (one GPU).
 //
-// MVTV_PRECOND_CHEB1 applies z = P(A) D^-1 r with A = D^-1 M and P of degree 1.  A degree-d Chebyshev polynomial needs about
-// (d+1) times fewer CG iterations than Jacobi (numpy prototype on 256^2, rho in {0.2, 3.2}: 1.9x, 2.8x, 3.6x, 4.5x for d = 1..4)
-// for 3 + 4(d-1) words per vertex instead of 3, i.e. 14 / 18 / 22 / 26 N words per iteration: 10 / 15 / 20 % less HBM traffic per
-// solve than degree 1, and fewer launches and grid reductions.  P is evaluated in Horner form, one stencil pass per degree:
-//     w_1 = c_d A z0 + c_{d-1} z0                      (FIRST: z0 = dinv r formed on the fly; reads r, dinv; writes w: 3 N)
+// z = P(A) D^-1 r with A = D^-1 M and P the degree-d Chebyshev polynomial (solver.cu, cheb_poly_coeffs).  Measured on 4096^2
+// (profiles/r2b_probe2.log): 34.8 / 24.2 / 18.6 / 14.9 CG iterations per pass for d = 1..4 (Jacobi: 65.9) and 11.0 / 10.3 / 9.9 /
+// 9.5 ms per pass.  P is evaluated in Horner form, one stencil pass per degree:
+//     w_1 = c_d A z0 + c_{d-1} z0                      (FIRST: z0 = dinv r formed on the fly; reads r, dinv; writes w: 3 N;
+//                                                       inside an x-update this pass is fused into k_cg_updprec2d)
 //     w_k = A w_{k-1} + c_{d-k} z0 ,  k = 2..d         (reads w, dinv, r; writes w: 4 N;  z = w_d)
-// with A w = w + rhoM dinv (K w - diag(K) w) (diag(c) is never read, as in k_cg_step2d).  w ping-pongs between the z buffer
-// and the q buffer (free between k_cg_update and the next k_cg_step), ending in z.  The last pass reduces r.z and commits it.
+// with A w = w + rhoM dinv (K w - diag(K) w) (diag(c) is never read, as in k_cg_step2d).  The pass outputs rotate over z, the idle
+// direction buffer and y (CgArgs::w_out_scr / w_in_scr), ending in z.  The last pass reduces r.z and commits it.
 // Structure as k_cg_step2d: a warp owns a strip of 64 vertices, x-neighbours by shuffle, marching along the last axis.
 #pragma once
 #include "cg_step2d.cuh"

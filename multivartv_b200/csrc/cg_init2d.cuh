@@ -1,5 +1,5 @@
 // k_cg_init2d: k_cg_init (kernels.cuh) for 2-D meshes in the marching / shuffle form of k_cg_step2d
-// (EXPERIMENTAL: opt-in with MVTV_INIT2D=1; logic-checked on the CPU SIMT emulator, not yet run on a GPU).
+// (the default on 2-D meshes with an even m0; 4096^2: 197 against 368 us, profiles/r2b_probe2.log).
 //   b = Oty + rho*(D^T alpha + uscale*D^T u)   (never stored)      r = b - (diag(c) + rhoM D^T D) theta      theta_old = theta
 //   r.z (z = dinv r), r.r, b.b                                      + the neighbours' ghost rows of r on several GPUs
 // k_cg_init gathers the 9 stencil points of theta per vertex (0.45 of the HBM peak on 4096^2: the re-reads go through L1 / L2);

@@ -333,7 +333,7 @@ struct CgArgs {
   // fused update + first preconditioner pass (k_cg_updprec*): r is updated OUT OF PLACE, the buffer holding the
   // current residual is selected by the parity of the iterations performed (r2 == nullptr: r is updated in place)
   T *r2 = nullptr;
-  int fold;        // peer path, EXPERIMENTAL (MVTV_FOLD_COMMIT=1): the reducing kernel's last thread also waits for the world's
+  int fold;        // peer path (default; MVTV_FOLD_COMMIT=0 turns it off): the reducing kernel's last thread also waits for the world's
                    // partials and commits the scalars, instead of a separate one-thread k_cg_peer_commit_* launch
 };
 
