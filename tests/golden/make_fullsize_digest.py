@@ -3,11 +3,11 @@
 box: the inputs come from bench.py's seeded generator) and a strided sample of theta and u -- every STRIDE-th vertex / row --
 is committed together with Counter, rho and the inner-iteration total.  The GPU test
 (tests/test_gpu_parity.py::test_large_mesh_digests) solves the same problem with the CUDA path and compares on the sample.
-Committed: cfg3_256 (configs[2]'s family on 256^3, n = 2^23) and cfg4_64 (configs[3]'s family on 64^4, n = N).  The full
+Committed: cfg3_256 (configs[2]'s family on 256^3, n = 2^23) and cfg4_48 (configs[3]'s family on 48^4, n = N).  The full
 512^3 / 96^4 meshes (names cfg3, cfg4) need ~60 GB of host memory for the oracle: generate them where that exists and the
 same test picks them up.
 
-    python tests/golden/make_fullsize_digest.py cfg3_256 cfg4_64 [cfg3] [cfg4] [--passes 3] [--threads 6]
+    python tests/golden/make_fullsize_digest.py cfg3_256 cfg4_48 [cfg3] [cfg4] [--passes 3] [--threads 6]
 """
 import os
 import sys
@@ -24,7 +24,7 @@ def main():
     from bench import WORKLOADS, synth_points
     from oracle import c_oracle as co
     # the full 512^3 / 96^4 meshes need ~60 GB and hours for the (memory-hungry) oracle; the same families one size down fit any box
-    WORKLOADS = dict(WORKLOADS, cfg3_256=dict(m=[256, 256, 256], n=1 << 23), cfg4_64=dict(m=[64, 64, 64, 64], n=64 ** 4))
+    WORKLOADS = dict(WORKLOADS, cfg3_256=dict(m=[256, 256, 256], n=1 << 23), cfg4_48=dict(m=[48, 48, 48, 48], n=48 ** 4))
     passes, threads, names = 3, 6, []
     argv = sys.argv[1:]
     while argv:

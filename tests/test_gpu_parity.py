@@ -610,9 +610,9 @@ def test_config3_config4_bounded_parity(mv):
     _fullsize_case(mv, [32, 32, 32, 32], 32 ** 4, 3, (mv.PRECOND_CHEB1, mv.PRECOND_AUTO))
 
 
-@pytest.mark.parametrize("name", ["cfg3_256", "cfg4_64", "cfg3", "cfg4"])
+@pytest.mark.parametrize("name", ["cfg3_256", "cfg4_48", "cfg3", "cfg4"])
 def test_large_mesh_digests(mv, name):
-    """BASELINE configs[2] / configs[3] (bench.py's inputs) on 256^3 with n = 2^23 and on 64^4 with n = N -- and on the full 512^3 /
+    """BASELINE configs[2] / configs[3] (bench.py's inputs) on 256^3 with n = 2^23 and on 48^4 with n = N -- and on the full 512^3 /
     96^4 meshes where their digests have been generated (the oracle needs ~60 GB for those) -- 3 RCPP passes of the CUDA path
     against the digest of the CPU oracle's run of the same problem (tests/golden/make_fullsize_digest.py: every 509th vertex of
     theta, every 3571st row of u, Counter, rho, sum(theta)): identical Counter, theta <= 1e-9, u <= 1e-8, rho equal."""
