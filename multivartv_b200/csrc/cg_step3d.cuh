@@ -98,16 +98,13 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   const int zhi = dt.has_hi ? dt.nz : dt.nz - 1;
   const int zfirst = zc0 - 1, zlast = zc1;
   const bool ghost_lo = (zc0 == 0 && dt.has_lo), ghost_hi = (zc1 == dt.nz && dt.has_hi);   // this CTA reads ghost planes
-  if (a.peer) {  // the neighbours fill our ghost planes directly: wait for the versions this launch needs
+  constexpr bool NEED_R = (MODE == STEP_JACOBI || MODE == STEP_PREC || MODE == STEP_UPDPREC);   // r's ghost planes (STEP_UPDPREC: posted
+                                                                                                // by the CG initialisation, kept up to date locally afterwards)
+  constexpr bool NEED_Z = (MODE == STEP_Z || MODE == STEP_HORNER || MODE == STEP_UPDPREC);      // z, w_{k-1}, q
+  if (a.peer && ghost_lo) {  // the neighbours fill our ghost planes directly: the plane BELOW is the first one of the march
     if (tid == 0) {
-      if (MODE == STEP_JACOBI || MODE == STEP_PREC || MODE == STEP_UPDPREC) {   // r (STEP_UPDPREC: posted by the CG initialisation,
-        if (ghost_lo) peer_spin(a.peer->hflag_from_prev, a.seq_halo, a.peer->error);   // kept up to date locally afterwards)
-        if (ghost_hi) peer_spin(a.peer->hflag_from_next, a.seq_halo, a.peer->error);
-      }
-      if (MODE == STEP_Z || MODE == STEP_HORNER || MODE == STEP_UPDPREC) {      // z, w_{k-1}, q
-        if (ghost_lo) peer_spin(a.peer->zflag_from_prev, a.seq_zin, a.peer->error);
-        if (ghost_hi) peer_spin(a.peer->zflag_from_next, a.seq_zin, a.peer->error);
-      }
+      if (NEED_R) peer_spin(a.peer->hflag_from_prev, a.seq_halo, a.peer->error);
+      if (NEED_Z) peer_spin(a.peer->zflag_from_prev, a.seq_zin, a.peer->error);
     }
     __syncthreads();
   }
@@ -129,6 +126,7 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   bool stored_peer = false;
   // ---- TMA staging (Cfg::TMAD >= 2): per-warp ring [stage][array][row][64] and one mbarrier per stage
   constexpr int TMAD = Cfg::TMAD;
+  static_assert(TMAD == 0 || MODE == STEP_INIT, "TMA staging prefetches planes ahead of the deferred peer-flag wait: STEP_INIT only");
   constexpr int NARR = Cfg::narr(MODE);
   constexpr int CSLOT = NARR - 1;                       // slot of the third array (p_old / q) when there is one
   MVTV_DYN_SMEM(smem_raw);
@@ -163,6 +161,13 @@ k_cg_step3d(const __grid_constant__ DimTab dt, const __grid_constant__ StencilTa
   for (int j = 0; j < RY; ++j) rcc[j][0] = rcc[j][1] = rdd[j][0] = rdd[j][1] = re1[j][0] = re1[j][1] = re2[j][0] = re2[j][1] = re3[j][0] = re3[j][1] = T(0);
   auto load_plane = [&](int zz) {
     if (zz > zlast) return;
+    if (a.peer && ghost_hi && zz == dt.nz) {   // the ghost plane ABOVE is the last one of the march: its flag is only needed now,
+      if (lane == 0) {                         // a late neighbour is hidden behind the whole chunk (each warp waits for itself)
+        if (NEED_R) peer_spin(a.peer->hflag_from_next, a.seq_halo, a.peer->error);
+        if (NEED_Z) peer_spin(a.peer->zflag_from_next, a.seq_zin, a.peer->error);
+      }
+      __syncwarp();
+    }
     const int zs = min(max(zz, zlo), zhi);
     const long long pb = (long long)(zs + 1) * dt.plane;
 #pragma unroll
