@@ -275,6 +275,7 @@ inline mvtv_solve_params default_params(int mode, double lambda) {
   p.mode = mode;
   p.lambda = lambda;
   p.rho_init = p.rho_matrix0 = p.tol = std::numeric_limits<double>::quiet_NaN();
+  p.precond = MVTV_PRECOND_AUTO;   // like the Python mirror: Jacobi for easy x-updates, the polynomial preconditioner otherwise
   return p;
 }
 
