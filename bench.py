@@ -438,9 +438,13 @@ def run_workload(mv, args, name, dist, rank, world, local_rank, precond, tag, st
                  "cg_update": ((fam + "<STEP_UPDPREC>") if fam == "k_cg_step3d" else "k_cg_updprec2d") if fusedk else "k_cg_update",
                  "cg_prec": (((fam + "<STEP_HORNER>") if fam == "k_cg_step3d" else "k_cg_horner2d") + " x %d per CG iteration" % (deg - 1)) if (fusedk and deg >= 2)
                             else fam + "<STEP_PREC>"}[dom]
+        # launches per launch group of the dominant class: the Horner passes 2..d of an iteration are timed as one group
+        lpg = (deg - 1) if (dom == "cg_prec" and fusedk and deg >= 2) else 1
+        traffic = ncu_traffic(name, dom, kernels, world, dtype)
         roof = {"bound": "hbm", "kernel": kname, "kernel_class": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": ncu_traffic(name, dom, kernels, world, dtype),
-                "alg_bytes_per_launch": stages[dom]["alg_bytes_per_launch_group"], "avg_launch_ms": stages[dom]["avg_ms"],
+                "frac": stages[dom]["frac"], "traffic": (traffic / lpg) if traffic else None,
+                "alg_bytes_per_launch": stages[dom]["alg_bytes_per_launch_group"] / lpg, "avg_launch_ms": stages[dom]["avg_ms"] / lpg,
+                "launches_per_cg_iteration": lpg,
                 "peak_source": peak_src, "share_of_step": stages[dom]["total_ms"] / max(tot_ms, 1e-9),
                 "pass": pass_fractions(Nl, Rl, esz, J, 1e3 * dev_s / passes, peak, moved)}
     return {

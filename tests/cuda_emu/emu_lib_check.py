@@ -159,13 +159,13 @@ def main():
 
     s2, s3, ring = "k_cg_step2d", "k_cg_step3d", "k_cg_step"
     R = {"MVTV_STEP": "ring"}
-    cases2 = [({}, "jacobi", s2, 0), ({}, "cheb1", s2, 1), ({}, "cheb2", s2, 2), ({}, "cheb3", s2, 3), ({}, "cheb4", s2, 4),
+    cases2 = [({}, "jacobi", s2, 0), ({}, "cheb1", s2, 1), ({}, "cheb2", s2, 2), ({}, "cheb3", s2, 3), ({}, "cheb4", s2, 4), ({}, "auto", s2, 3),
               (R, "jacobi", ring, 0), (R, "cheb1", ring, 1), (R, "cheb3", ring, 1),
               ({"EMU_NSM": "1", "EMU_OCC": "1"}, "cheb3", s2, 3), ({"EMU_NSM": "16", "EMU_OCC": "4"}, "cheb2", s2, 2),
               ({"MVTV_ZU_KERNEL": "gather"}, "cheb1", s2, 1)]
-    sweep([66, 40], 2500, 1, 3, cases2[:7] if quick else cases2)
+    sweep([66, 40], 2500, 1, 3, cases2[:8] if quick else cases2)
     if not quick:
-        sweep([130, 33], 3000, 7, 2, [cases2[1], cases2[3], cases2[6]])
+        sweep([130, 33], 3000, 7, 2, [cases2[1], cases2[3], cases2[7]])
     cases3 = [({}, "jacobi", s3, 0), ({}, "cheb1", s3, 1), ({}, "cheb2", s3, 2), ({}, "cheb3", s3, 3), ({}, "cheb4", s3, 4),
               (R, "jacobi", ring, 0), (R, "cheb1", ring, 1), ({"EMU_NSM": "16"}, "cheb3", s3, 3), ({"EMU_NSM": "2", "EMU_OCC": "1"}, "cheb2", s3, 2),
               ({"MVTV_TUNE": "init3d=0"}, "jacobi", s3, 0), ({"MVTV_TUNE": "fused=0"}, "cheb1", s3, 1), ({"MVTV_TUNE": "init3d=0"}, "cheb3", s3, 3),

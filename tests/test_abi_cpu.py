@@ -127,3 +127,25 @@ def test_bench_reference_arm_contract():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(env, RANK="1", WORLD_SIZE="2"))
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_bench_byte_accounting_matches_design():
+    """bench.py's algorithmic bytes per kernel class add up to the per-pass formulas of DESIGN.md section 3:
+    T [(2R+4N) + 8N + 13 N J] with Jacobi, T [(2R+4N) + 8N + (3+4(d-1)) N + (13+4(d-1)) N J] with the fused degree-d polynomial."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    N, R, J = 1000, 6980, 40
+    strip = {"cg_prec_words": 3, "fused_update": 1}
+    tot, perf = bench.stage_totals(N, R, 8, 1, J, 0, strip)
+    assert sum(tot.values()) == 8 * ((2 * R + 4 * N) + 8 * N + 13 * N * J) and perf["cg_prec"] == 0
+    for d in (1, 2, 3, 4):
+        tot, perf = bench.stage_totals(N, R, 8, 1, J, d, strip)
+        assert sum(tot.values()) == 8 * ((2 * R + 4 * N) + 8 * N + (3 + 4 * (d - 1)) * N + (13 + 4 * (d - 1)) * N * J)
+        assert perf["cg_step"] == J and perf["cg_update"] == J and perf["cg_prec"] == 1 + (J if d >= 2 else 0)
+    ring = {"cg_prec_words": 4, "fused_update": 0}
+    tot, _ = bench.stage_totals(N, R, 8, 1, J, 1, ring)          # ring kernels: 5 N + 6 N + 4 N per iteration
+    assert sum(tot.values()) == 8 * ((2 * R + 4 * N) + 8 * N + 15 * N * J)
+    f = bench.pass_fractions(N, R, 8, J, 1.0, 6545.0, sum(tot.values()))
+    assert f["alg_bytes"] == 8 * ((2 * R + 3 * N) + 12 * N * J) and abs(f["frac_of_8TBs"] * 8000.0 - f["gbs"]) < 1e-9
