@@ -1242,6 +1242,7 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
   bool first_prec_done = false;
   int launched = 0;
   int batch = std::max(2, std::min(last_cg_iters, 256));
+  const int follow = std::max(2, std::min(batch / 4 + 1, 16));   // size of the follow-up batches
   double iters = 0;
   for (;;) {
     for (int k = 0; k < batch; ++k) {
@@ -1286,7 +1287,9 @@ int mvtv_plan::cg_solve(double rho, double usc, double rhoM, double rtol, int ma
       if (sizeof(T) == 8) status = MVTV_ERR_INNER_SOLVE;
       break;
     }
-    batch = std::max(2, std::min({batch, 64, maxit - launched}));
+    // the first batch is sized from the previous x-update; a solve that needs a few iterations more gets small follow-up batches
+    // (launches after convergence are no-ops, but each still costs a launch)
+    batch = std::max(1, std::min(follow, maxit - launched));
   }
   inner += (long long)iters;
   last_cg_iters = (int)iters + 1;
